@@ -1,0 +1,164 @@
+/*
+ * sterne_b200 -- C ABI of the B200-native astrometric log-likelihood hot path.
+ *
+ * Drop-in boundary for dingswin/sterne's likelihood path.  The reference has no
+ * native code and no FFI of its own (pure Python); the entry points below are what
+ * a ctypes binding inside the reference's `Gaussianlikelihood` (simulate.py:325-384)
+ * and `positions` (model/positions.py:13-30) would bind.  Plain pointers and sizes
+ * only; no torch / CUDA types in the signatures (streams travel as void*).
+ *
+ * All functions return 0 on success or a negative StnStatus; they never throw.
+ * stn_last_error() gives a thread-local description of the last failure.
+ *
+ * Ownership: the caller owns every buffer it passes in.  The library owns only the
+ * context (device copies of the epoch tables made by stn_create, plus staging
+ * buffers used by the *_host entry points).  A context is immutable after creation
+ * and may be used from one thread at a time.
+ */
+#ifndef STERNE_B200_H
+#define STERNE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STN_ABI_VERSION 1
+
+/* Parameter roots in the reference's fixed alphabetical order
+ * (priors.py:270, positions.py:56).  StnSource.col[] is indexed by these. */
+enum StnRoot {
+    STN_DEC = 0, STN_EFAC = 1, STN_EFAD = 2, STN_INCL = 3, STN_MU_A = 4,
+    STN_MU_D = 5, STN_OM_ASC = 6, STN_PX = 7, STN_RA = 8, STN_NROOTS = 9
+};
+
+/* The reference's "parameter switched off" sentinel (positions.py:59). */
+#define STN_SENTINEL (-999.0)
+
+enum StnStatus {
+    STN_OK = 0,
+    STN_ERR_INVALID = -1,   /* bad argument / inconsistent problem description */
+    STN_ERR_CUDA = -2,      /* a CUDA runtime call failed (message has the CUDA error) */
+    STN_ERR_NOMEM = -3,
+    STN_ERR_DEVICE = -4     /* no usable sm_100 device */
+};
+
+enum StnLayout {
+    STN_LAYOUT_AOS = 0,     /* theta[n*ld + p] : (N, P) row-major, ld >= P  (sampler-native) */
+    STN_LAYOUT_SOA = 1      /* theta[p*ld + n] : (P, N), ld >= N            (coalesced loads) */
+};
+
+enum StnMode {
+    STN_MODE_FAST = 0,      /* hoisted per-(sample,source) coefficients, FMA, reciprocals */
+    STN_MODE_STRICT = 1     /* the reference's operation order, one rounding per operation
+                               (positions.py:108-120,308-309; simulate.py:317-320,368-371) */
+};
+
+/* Per-epoch row of the FAST table: STN_FAST_ROW doubles, 16-byte aligned pairs.
+ *  [0] dT = (epoch - refepoch) * d->yr   (positions.py:108)
+ *  [1] X  [2] Y  [3] Z   Earth wrt SSB, AU, ICRS (positions.py:305)
+ *  [4] observed RA (rad)   [5] observed Dec (rad)      (simulate.py:217)
+ *  EFAC off: [6] 1/err_ra  [7] 1/err_dec  [8],[9] unused (0)
+ *  EFAC on : [6] err_random_ra^2 [7] err_random_dec^2 [8] err_sys_ra^2 [9] err_sys_dec^2
+ *                                                   (simulate.py:317)
+ *  [10] b_AU*cos(theta)  [11] b_AU*sin(theta)   orbit terms, 0 when no parfile
+ *                                                   (reflex_motion.py:187-200)
+ */
+#define STN_FAST_ROW 12
+
+/* Per-epoch row of the STRICT table: STN_STRICT_ROW doubles.
+ *  [0] dT [1] X [2] Y [3] Z [4] obs RA [5] obs Dec
+ *  [6] err_ra [7] err_dec                    (EFAC off: VLBI 'errs')
+ *  [8] err_random_ra [9] err_random_dec [10] err_sys_ra [11] err_sys_dec   (EFAC on)
+ *  [12] b_AU [13] cos(theta) [14] sin(theta) [15] unused
+ */
+#define STN_STRICT_ROW 16
+
+typedef struct StnSource {
+    int64_t n_epochs;
+    const double* fast_rows;     /* host, n_epochs * STN_FAST_ROW   */
+    const double* strict_rows;   /* host, n_epochs * STN_STRICT_ROW */
+    int32_t col[STN_NROOTS];     /* theta column of each root for this source, -1 = absent
+                                    (positions.py:32-60 routing, resolved once) */
+    int32_t efac_on;             /* 1: rows carry err_random/err_sys and col[STN_EFAC] >= 0 */
+    int32_t binary;              /* 1: a parfile was given (dict_timing != {}), orbit terms valid */
+    double cos_decj;             /* cos(DECJ of the parfile)  (reflex_motion.py:212) */
+    double neg_sum_log_err;      /* -sum(log(errs)) over 2E terms, used when EFAC is off
+                                    (simulate.py:371; parameter-independent) */
+    double a1_lts;               /* A1 in lt-s for the a1dot constraint (kopeikin_effects.py:61) */
+} StnSource;
+
+typedef struct StnProblem {
+    int32_t n_sources;
+    int32_t n_params;            /* P: number of theta columns */
+    const StnSource* sources;
+    /* a1dot Gaussian constraints (simulate.py:373-377), already broadcast on the host:
+       term k uses source a1dot_source[k], mean a1dot_mu[k], sigma a1dot_sigma[k]. */
+    int32_t n_a1dot;
+    const int32_t* a1dot_source;
+    const double* a1dot_mu;
+    const double* a1dot_sigma;
+    /* sin(incl) Gaussian constraints (simulate.py:379-383): theta column, mean, sigma. */
+    int32_t n_sini;
+    const int32_t* sini_col;
+    const double* sini_mu;
+    const double* sini_sigma;
+} StnProblem;
+
+typedef struct StnCtx StnCtx;
+
+int stn_version(void);
+const char* stn_last_error(void);
+
+/* Copies the problem to `device` (epoch tables, routing, constraints).
+ * Replaces: Gaussianlikelihood.__init__ (simulate.py:326-358). */
+int stn_create(const StnProblem* problem, int device, StnCtx** out_ctx);
+int stn_destroy(StnCtx* ctx);
+
+/* Batched log-likelihood, device buffers.
+ * Replaces: Gaussianlikelihood.log_likelihood (simulate.py:362-384) evaluated for
+ * n parameter vectors.  theta_dev: n vectors of P doubles in `layout` with leading
+ * dimension ld; out_dev: n doubles.  lanes = 0 lets the library choose how many
+ * lanes of a warp share one sample (1,2,4,...,32); pass an explicit value to make
+ * results independent of how a batch is sharded.  Asynchronous on `stream`
+ * (a cudaStream_t, NULL = default stream). */
+int stn_loglike(StnCtx* ctx, const double* theta_dev, int64_t n, int64_t ld,
+                int layout, int mode, int lanes, double* out_dev, void* stream);
+
+/* Same, HOST buffers: H2D copy, kernel(s), D2H copy, synchronised on return.
+ * Large batches are cut into chunks whose copies overlap the kernels.  Pinned
+ * buffers (stn_host_alloc) are copied at full PCIe rate. */
+int stn_loglike_host(StnCtx* ctx, const double* theta_host, int64_t n, int64_t ld,
+                     int layout, int mode, int lanes, double* out_host);
+
+/* Model positions of one source for n parameter vectors.
+ * Replaces: positions() (positions.py:13-30) -> radec_dev[n][2E] = concat(ra[E], dec[E]) rad;
+ * off_mas_dev (nullable) receives the offsets in mas (positions.py:114-118). */
+int stn_model(StnCtx* ctx, int source, const double* theta_dev, int64_t n, int64_t ld,
+              int layout, int mode, double* radec_dev, double* off_mas_dev, void* stream);
+
+/* Choice stn_loglike(lanes = 0) would make for a batch of n. */
+int stn_auto_lanes(StnCtx* ctx, int64_t n);
+
+/* Number of kernel launches issued through this context so far. */
+int64_t stn_launch_count(StnCtx* ctx);
+
+/* Pinned host memory for the *_host entry points. */
+int stn_host_alloc(void** ptr, int64_t bytes);
+int stn_host_free(void* ptr);
+
+/* FP64 pipe peak (dependent-free DFMA streams on every SM); the roofline denominator.
+ * Runs `reps` launches of `iters` FMA rounds, returns the best TFLOP/s and its time. */
+int stn_fp64_peak(int device, int iters, int reps, double* tflops, double* ms);
+
+/* Timing helper for bench.py: runs `steps` back-to-back stn_loglike launches on an
+ * internal stream bracketed by CUDA events on that stream; returns total ms. */
+int stn_loglike_timed(StnCtx* ctx, const double* theta_dev, int64_t n, int64_t ld,
+                      int layout, int mode, int lanes, double* out_dev, int steps,
+                      double* total_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STERNE_B200_H */

@@ -1,0 +1,991 @@
+// sterne_b200.cu -- B200 (sm_100a) kernels and C ABI for the astrometric log-likelihood.
+//
+// Path replaced (reference file:line, /root/reference/src/sterne/):
+//   simulate.py:362-384   Gaussianlikelihood.log_likelihood
+//   simulate.py:303-320   adjust_errs_with_efac
+//   model/positions.py:13-121,266-310   positions / position / parallax offset
+//   model/reflex_motion.py:201-214      (Omega_asc, incl) rotation of the orbit terms
+//   model/kopeikin_effects.py:11-45     a1dot from proper motion
+//
+// Design (DESIGN.md has the long form):
+//   * one thread owns R samples (R = 1 or 2) and L lanes of a warp may share one sample
+//     (L = 1..32, epochs interleaved across the lanes, fixed-order shuffle reduction);
+//   * per (sample, source) prologue turns the 9 routed parameters into FMA coefficients
+//     (two sincos + one reciprocal); the epoch loop is then pure DFMA/DMUL/DADD;
+//   * the parameter-independent epoch table streams L2 -> shared memory through the
+//     bulk async-copy engine (cp.async.bulk + mbarrier, SASS: UBLKCP), double buffered,
+//     and every lane reads the same row (shared-memory broadcast, LDS.128);
+//   * FP64 throughout, no tensor cores (not a contraction).
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 (see build.py).
+
+#include "sterne_b200.h"
+
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <cmath>
+#include <new>
+#include <string>
+#include <vector>
+
+// ---------------------------------------------------------------------------------
+// constants (astropy unit factors; see sterne_b200/constants.py for provenance)
+// ---------------------------------------------------------------------------------
+#define STN_MAS2RAD   4.84813681109536e-09          /* (pi/180)/3600*0.001 */
+#define STN_DEG2RAD   0.017453292519943295
+#define STN_MASYR2RADS (4.84813681109536e-09 / (365.25 * 86400.0))
+#define STN_LN2       0.6931471805599453
+
+namespace {
+
+constexpr int kThreads = 256;      // threads per CTA of the likelihood kernels
+constexpr int kChunk = 128;        // epochs per shared-memory stage (128 * 96 B = 12 KiB)
+constexpr int kStages = 2;
+constexpr int kFirst = 1, kLast = 2;
+
+struct SrcDev {
+    const double* fast_rows;
+    const double* strict_rows;
+    int n_epochs;
+    int col[STN_NROOTS];
+    int efac_on;
+    int binary;
+    double cos_decj;
+    double inv_cos_decj;
+    double neg_sum_log_err;
+    double a1_lts;
+};
+
+struct ChunkDev {
+    const double* rows;   // device pointer into the source's fast table
+    int n_epochs;
+    int source;
+    int flags;            // kFirst | kLast
+    int pad;
+};
+
+struct ProbDev {
+    int n_sources, n_params, n_chunks, n_a1dot, n_sini;
+    const SrcDev* src;
+    const ChunkDev* chunks;
+    const int* a1_src;
+    const double* a1_mu;
+    const double* a1_sigma;
+    const int* sini_col;
+    const double* sini_mu;
+    const double* sini_sigma;
+};
+
+// ---------------------------------------------------------------------------------
+// small PTX wrappers: mbarrier + bulk async copy (TMA engine, 1-D form)
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// fill one stage with `n_epochs` rows (an empty chunk just completes the phase)
+__device__ __forceinline__ void stage_fill(double* dst, const double* src, int n_epochs, uint64_t* bar) {
+    const uint32_t bytes = (uint32_t)n_epochs * STN_FAST_ROW * (uint32_t)sizeof(double);
+    if (bytes != 0) {
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(dst, src, bytes, bar);
+    } else {
+        mbar_arrive(bar);
+    }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    const uint32_t addr = smem_u32(bar);
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+// ---------------------------------------------------------------------------------
+// parameter fetch (routing table resolved on the host: positions.py:32-60)
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ double load_param(const double* __restrict__ theta, int64_t n, int col,
+                                             int64_t ld, int layout) {
+    if (col < 0) return STN_SENTINEL;
+    return layout == STN_LAYOUT_SOA ? __ldg(theta + (int64_t)col * ld + n)
+                                    : __ldg(theta + n * ld + col);
+}
+
+struct Params {
+    double dec, efac, efad, incl, mu_a, mu_d, om_asc, px, ra;
+};
+
+__device__ __forceinline__ Params load_params(const SrcDev& S, const double* __restrict__ theta,
+                                              int64_t n, int64_t ld, int layout) {
+    Params p;
+    p.dec = load_param(theta, n, S.col[STN_DEC], ld, layout);
+    p.efac = load_param(theta, n, S.col[STN_EFAC], ld, layout);
+    p.efad = load_param(theta, n, S.col[STN_EFAD], ld, layout);
+    p.incl = load_param(theta, n, S.col[STN_INCL], ld, layout);
+    p.mu_a = load_param(theta, n, S.col[STN_MU_A], ld, layout);
+    p.mu_d = load_param(theta, n, S.col[STN_MU_D], ld, layout);
+    p.om_asc = load_param(theta, n, S.col[STN_OM_ASC], ld, layout);
+    p.px = load_param(theta, n, S.col[STN_PX], ld, layout);
+    p.ra = load_param(theta, n, S.col[STN_RA], ld, layout);
+    return p;
+}
+
+// ---------------------------------------------------------------------------------
+// FAST form: per-(sample, source) coefficients, mas->rad folded in.
+//   offK_ra  = dT*c0 + X*c1 + Y*c2 [+ Bc*r0c + Bs*r0s]
+//   offK_dec = dT*mud + X*d1 + Y*d2 + Z*d3 [+ Bc*r1c + Bs*r1s]
+// which is positions.py:110-111,308-309 and reflex_motion.py:201-214 with the
+// divisions and trig hoisted out of the epoch loop.
+// ---------------------------------------------------------------------------------
+struct Coef {
+    double ra, dec;
+    double c0, c1, c2;
+    double mud, d1, d2, d3;
+    double r0c, r0s, r1c, r1s;
+    double g_ra, g_dec;   // EFAC: efac^2 and (efac*efad)^2
+};
+
+__device__ __forceinline__ Coef make_coef(const SrcDev& S, const Params& p) {
+    Coef c;
+    const double K = STN_MAS2RAD;
+    double sd, cd, sa, ca;
+    sincos(p.dec, &sd, &cd);
+    sincos(p.ra, &sa, &ca);
+    const double icd = 1.0 / cd;
+    const bool px_on = (p.px != STN_SENTINEL);            // positions.py:115
+    const double pxe = px_on ? p.px : 0.0;
+    c.ra = p.ra;
+    c.dec = p.dec;
+    c.c0 = (p.mu_a * icd) * K;
+    c.c1 = (pxe * sa * icd) * K;
+    c.c2 = -(pxe * ca * icd) * K;
+    c.mud = p.mu_d * K;
+    c.d1 = (pxe * ca * sd) * K;
+    c.d2 = (pxe * sa * sd) * K;
+    c.d3 = -(pxe * cd) * K;
+    const bool rf_on = px_on && S.binary && (p.incl != STN_SENTINEL) &&
+                       (p.om_asc != STN_SENTINEL);        // positions.py:117
+    if (rf_on) {
+        double sO, cO;
+        sincos(p.om_asc * STN_DEG2RAD, &sO, &cO);
+        const double ci = cos(p.incl);
+        const double pk = pxe * K;
+        c.r0c = pk * sO * S.inv_cos_decj;
+        c.r0s = pk * (cO * ci) * S.inv_cos_decj;
+        c.r1c = pk * cO;
+        c.r1s = -(pk * (sO * ci));
+    } else {
+        c.r0c = c.r0s = c.r1c = c.r1s = 0.0;
+    }
+    if (S.efac_on) {
+        // simulate.py:311-317; a sampled efac of exactly -999 switches EFAC off for that
+        // vector (errs^2 is then err_random^2 + err_sys^2 up to rounding).
+        const double ef = (p.efac != STN_SENTINEL) ? p.efac : 1.0;
+        const double ed = (p.efad != STN_SENTINEL && p.efac != STN_SENTINEL) ? p.efad : 1.0;
+        c.g_ra = ef * ef;
+        const double t = ef * ed;
+        c.g_dec = t * t;
+    } else {
+        c.g_ra = c.g_dec = 1.0;
+    }
+    return c;
+}
+
+template <bool BIN>
+__device__ __forceinline__ void fast_offsets(const Coef& c, const double2 tx, const double2 yz,
+                                             const double2 bc, double& ora, double& odec) {
+    ora = tx.x * c.c0;
+    ora = fma(tx.y, c.c1, ora);
+    ora = fma(yz.x, c.c2, ora);
+    odec = tx.x * c.mud;
+    odec = fma(tx.y, c.d1, odec);
+    odec = fma(yz.x, c.d2, odec);
+    odec = fma(yz.y, c.d3, odec);
+    if (BIN) {
+        ora = fma(bc.x, c.r0c, ora);
+        ora = fma(bc.y, c.r0s, ora);
+        odec = fma(bc.x, c.r1c, odec);
+        odec = fma(bc.y, c.r1s, odec);
+    }
+}
+
+// 1/v for positive normal v: MUFU.RCP64H seed + one cubic step (relative error ~1e-16).
+__device__ __forceinline__ double fast_rcp(double v) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(v));
+    const double e = fma(-v, y, 1.0);
+    const double p = fma(e, e, e);
+    return fma(y, p, y);
+}
+
+// split a positive normal double into mantissa in [1,2) and unbiased exponent
+__device__ __forceinline__ double split_exp(double v, int& esum) {
+    const int hi = __double2hiint(v);
+    esum += (hi >> 20) - 1023;
+    return __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(v));
+}
+
+struct Acc {
+    double chi_ra, chi_dec;   // sum of (res/sigma)^2 per coordinate
+    double prod;              // EFAC: running product of variance mantissas
+    int esum;                 // EFAC: running sum of variance exponents
+};
+
+template <int R, int L, bool EF, bool BIN>
+__device__ __forceinline__ void epoch_loop(const double* __restrict__ rows, int n_epochs, int sub,
+                                           const Coef (&cf)[R], Acc (&acc)[R]) {
+#pragma unroll 2
+    for (int e = sub; e < n_epochs; e += L) {
+        const double2* row = reinterpret_cast<const double2*>(rows + e * STN_FAST_ROW);
+        const double2 tx = row[0];
+        const double2 yz = row[1];
+        const double2 ob = row[2];
+        const double2 aa = row[3];
+        double2 bb = make_double2(0.0, 0.0), bc = make_double2(0.0, 0.0);
+        if (EF) bb = row[4];
+        if (BIN) bc = row[5];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            double ora, odec;
+            fast_offsets<BIN>(cf[r], tx, yz, bc, ora, odec);
+            // model = ref + offset (rad); residual = obs - model   (positions.py:119-120,
+            // simulate.py:368).  This order is kept: the subtraction cancels ~9 digits.
+            const double res_ra = ob.x - (cf[r].ra + ora);
+            const double res_dec = ob.y - (cf[r].dec + odec);
+            if (!EF) {
+                const double z_ra = res_ra * aa.x;
+                const double z_dec = res_dec * aa.y;
+                acc[r].chi_ra = fma(z_ra, z_ra, acc[r].chi_ra);
+                acc[r].chi_dec = fma(z_dec, z_dec, acc[r].chi_dec);
+            } else {
+                const double v_ra = fma(cf[r].g_ra, bb.x, aa.x);     // simulate.py:317
+                const double v_dec = fma(cf[r].g_dec, bb.y, aa.y);
+                const double w_ra = fast_rcp(v_ra);
+                const double w_dec = fast_rcp(v_dec);
+                acc[r].chi_ra = fma(res_ra * res_ra, w_ra, acc[r].chi_ra);
+                acc[r].chi_dec = fma(res_dec * res_dec, w_dec, acc[r].chi_dec);
+                acc[r].prod *= split_exp(v_ra, acc[r].esum);
+                acc[r].prod *= split_exp(v_dec, acc[r].esum);
+            }
+        }
+    }
+    if (EF) {
+        // at most 2*kChunk mantissas in [1,2) were multiplied: renormalise
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r].prod = split_exp(acc[r].prod, acc[r].esum);
+    }
+}
+
+template <int L>
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// a1dot (kopeikin_effects.py:41-45) and sin(incl) (simulate.py:379-383) Gaussian terms
+__device__ double constraint_terms(const ProbDev& P, const double* __restrict__ theta, int64_t n,
+                                   int64_t ld, int layout) {
+    double add = 0.0;
+    if (P.n_a1dot > 0) {
+        double s = 0.0;
+        for (int k = 0; k < P.n_a1dot; ++k) {
+            const SrcDev& S = P.src[P.a1_src[k]];
+            const double inc = load_param(theta, n, S.col[STN_INCL], ld, layout);
+            const double mu_a = load_param(theta, n, S.col[STN_MU_A], ld, layout);
+            const double mu_d = load_param(theta, n, S.col[STN_MU_D], ld, layout);
+            const double om = load_param(theta, n, S.col[STN_OM_ASC], ld, layout);
+            const double mu = sqrt(mu_a * mu_a + mu_d * mu_d);
+            const double th = atan2(mu_a, mu_d);
+            double v = mu * sin(th - om * STN_DEG2RAD) / tan(inc);
+            v = (v * S.a1_lts) * STN_MASYR2RADS;
+            const double z = (v - P.a1_mu[k]) / P.a1_sigma[k];
+            s += z * z;
+        }
+        add += -0.5 * s;
+    }
+    for (int k = 0; k < P.n_sini; ++k) {
+        const double x = load_param(theta, n, P.sini_col[k], ld, layout);
+        const double z = (P.sini_mu[k] - sin(x)) / P.sini_sigma[k];
+        add += -0.5 * (z * z);
+    }
+    return add;
+}
+
+// ---------------------------------------------------------------------------------
+// K1: fused FAST log-likelihood
+// ---------------------------------------------------------------------------------
+template <int R, int L>
+__global__ void __launch_bounds__(kThreads)
+stn_loglike_fast_kernel(const ProbDev P, const double* __restrict__ theta, const int64_t N,
+                        const int64_t ld, const int layout, double* __restrict__ out) {
+    __shared__ __align__(128) double stage[kStages][kChunk * STN_FAST_ROW];
+    __shared__ __align__(8) uint64_t full[kStages];
+
+    const int tid = threadIdx.x;
+    const int sub = tid % L;
+    const int grp = tid / L;
+    constexpr int G = kThreads / L;                     // sample groups per CTA
+    const int64_t tile_base = (int64_t)blockIdx.x * (G * R);
+
+    int64_t nidx[R];
+    bool valid[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int64_t n = tile_base + (int64_t)r * G + grp;
+        valid[r] = n < N;
+        nidx[r] = valid[r] ? n : (N - 1);
+    }
+
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0 && P.n_chunks > 0) {
+        const ChunkDev c0 = P.chunks[0];
+        stage_fill(stage[0], c0.rows, c0.n_epochs, &full[0]);
+    }
+
+    double logl[R];
+    Coef cf[R];
+    Acc acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) logl[r] = 0.0;
+
+    for (int c = 0; c < P.n_chunks; ++c) {
+        const ChunkDev ck = P.chunks[c];
+        if (tid == 0 && c + 1 < P.n_chunks) {
+            // stage (c+1)&1 was last read in iteration c-1; the __syncthreads that ended it
+            // ordered those reads before this refill.
+            const ChunkDev nx = P.chunks[c + 1];
+            stage_fill(stage[(c + 1) & 1], nx.rows, nx.n_epochs, &full[(c + 1) & 1]);
+        }
+        const SrcDev& S = P.src[ck.source];
+        if (ck.flags & kFirst) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const Params p = load_params(S, theta, nidx[r], ld, layout);
+                cf[r] = make_coef(S, p);
+                acc[r].chi_ra = 0.0;
+                acc[r].chi_dec = 0.0;
+                acc[r].prod = 1.0;
+                acc[r].esum = 0;
+            }
+        }
+        mbar_wait(&full[c & 1], (uint32_t)((c >> 1) & 1));
+        const double* rows = stage[c & 1];
+        const bool ef = S.efac_on != 0;
+        const bool bin = S.binary != 0;
+        if (!ef && !bin) epoch_loop<R, L, false, false>(rows, ck.n_epochs, sub, cf, acc);
+        else if (ef && !bin) epoch_loop<R, L, true, false>(rows, ck.n_epochs, sub, cf, acc);
+        else if (!ef && bin) epoch_loop<R, L, false, true>(rows, ck.n_epochs, sub, cf, acc);
+        else epoch_loop<R, L, true, true>(rows, ck.n_epochs, sub, cf, acc);
+
+        if (ck.flags & kLast) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                // log_p += -0.5*sum((res/errs)^2); log_p += -sum(log(errs))  (simulate.py:370-371)
+                const double chi = group_sum<L>(acc[r].chi_ra + acc[r].chi_dec);
+                double logdet;
+                if (ef) {
+                    // -sum(log sigma) = -0.5 * log(prod of variances)
+                    const double part = log(acc[r].prod) + (double)acc[r].esum * STN_LN2;
+                    logdet = -0.5 * group_sum<L>(part);
+                } else {
+                    logdet = S.neg_sum_log_err;
+                }
+                logl[r] += -0.5 * chi;
+                logl[r] += logdet;
+            }
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (P.n_a1dot > 0 || P.n_sini > 0) logl[r] += constraint_terms(P, theta, nidx[r], ld, layout);
+        if (valid[r] && sub == 0) out[nidx[r]] = logl[r];
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// STRICT form: the reference's operation order, one IEEE rounding per operation
+// (the __d*_rn intrinsics are never contracted into FMAs).
+// ---------------------------------------------------------------------------------
+struct StrictTrig {
+    double sd, cd, sa, ca, sO, cO, ci;
+    bool px_on, rf_on;
+};
+
+__device__ __forceinline__ StrictTrig strict_trig(const SrcDev& S, const Params& p) {
+    StrictTrig t;
+    t.sd = sin(p.dec);
+    t.cd = cos(p.dec);
+    t.sa = sin(p.ra);
+    t.ca = cos(p.ra);
+    t.px_on = (p.px != STN_SENTINEL);
+    t.rf_on = t.px_on && S.binary && (p.incl != STN_SENTINEL) && (p.om_asc != STN_SENTINEL);
+    t.sO = t.cO = t.ci = 0.0;
+    if (t.rf_on) {
+        const double Om = __dmul_rn(p.om_asc, STN_DEG2RAD);
+        t.sO = sin(Om);
+        t.cO = cos(Om);
+        t.ci = cos(p.incl);
+    }
+    return t;
+}
+
+// offsets in mas for one epoch (positions.py:108-118, 308-309; reflex_motion.py:201-214)
+__device__ __forceinline__ void strict_offsets(const SrcDev& S, const Params& p, const StrictTrig& t,
+                                               const double* __restrict__ row, double& ora,
+                                               double& odec) {
+    const double dT = row[0], X = row[1], Y = row[2], Z = row[3];
+    ora = __ddiv_rn(__dmul_rn(dT, p.mu_a), t.cd);
+    odec = __dmul_rn(dT, p.mu_d);
+    if (t.px_on) {
+        const double a = __dsub_rn(__dmul_rn(X, t.sa), __dmul_rn(Y, t.ca));
+        const double pra = __ddiv_rn(__dmul_rn(p.px, a), t.cd);
+        double b = __dadd_rn(__dmul_rn(__dmul_rn(X, t.ca), t.sd), __dmul_rn(__dmul_rn(Y, t.sa), t.sd));
+        b = __dsub_rn(b, __dmul_rn(Z, t.cd));
+        const double pdec = __dmul_rn(p.px, b);
+        ora = __dadd_rn(ora, pra);
+        odec = __dadd_rn(odec, pdec);
+        if (t.rf_on) {
+            const double offset = __dmul_rn(row[12], p.px);
+            const double m0 = __dmul_rn(offset, row[13]);
+            const double m1 = __dmul_rn(offset, row[14]);
+            const double b0 = __dadd_rn(__dmul_rn(t.sO, m0), __dmul_rn(__dmul_rn(t.cO, t.ci), m1));
+            const double b1 = __dadd_rn(__dmul_rn(t.cO, m0), __dmul_rn(-__dmul_rn(t.sO, t.ci), m1));
+            ora = __dadd_rn(ora, __ddiv_rn(b0, S.cos_decj));
+            odec = __dadd_rn(odec, b1);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+stn_loglike_strict_kernel(const ProbDev P, const double* __restrict__ theta, const int64_t N,
+                          const int64_t ld, const int layout, double* __restrict__ out) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    double logl = 0.0;
+    for (int s = 0; s < P.n_sources; ++s) {
+        const SrcDev& S = P.src[s];
+        const Params p = load_params(S, theta, n, ld, layout);
+        const StrictTrig t = strict_trig(S, p);
+        const bool ef_on = S.efac_on && (p.efac != STN_SENTINEL);
+        const double efad = (p.efad != STN_SENTINEL) ? p.efad : 1.0;
+        double chi = 0.0, slog = 0.0;
+        // RA half then Dec half, as in the concatenated [RA..., Dec...] vectors
+        for (int half = 0; half < 2; ++half) {
+            for (int e = 0; e < S.n_epochs; ++e) {
+                const double* row = S.strict_rows + (int64_t)e * STN_STRICT_ROW;
+                double ora, odec;
+                strict_offsets(S, p, t, row, ora, odec);
+                const double ref = half == 0 ? p.ra : p.dec;
+                const double off = half == 0 ? ora : odec;
+                const double model = __dadd_rn(ref, __dmul_rn(off, STN_MAS2RAD));
+                const double res = __dsub_rn(row[4 + half], model);
+                double err;
+                if (S.efac_on) {
+                    if (ef_on) {
+                        const double f = half == 0 ? __dmul_rn(p.efac, 1.0) : __dmul_rn(p.efac, efad);
+                        const double q = __dmul_rn(f, row[10 + half]);
+                        const double v = __dadd_rn(__dmul_rn(row[8 + half], row[8 + half]), __dmul_rn(q, q));
+                        err = __dsqrt_rn(v);
+                    } else {
+                        // efac sampled as exactly -999: errs^2 ~ err_random^2 + err_sys^2
+                        const double v = __dadd_rn(__dmul_rn(row[8 + half], row[8 + half]),
+                                                   __dmul_rn(row[10 + half], row[10 + half]));
+                        err = __dsqrt_rn(v);
+                    }
+                    slog = __dadd_rn(slog, log(err));
+                } else {
+                    err = row[6 + half];   // sqrt(errs^2) == errs
+                }
+                const double z = __ddiv_rn(res, err);
+                chi = __dadd_rn(chi, __dmul_rn(z, z));
+            }
+        }
+        logl = __dadd_rn(logl, __dmul_rn(-0.5, chi));
+        logl = __dadd_rn(logl, S.efac_on ? -slog : S.neg_sum_log_err);
+    }
+    if (P.n_a1dot > 0 || P.n_sini > 0) logl += constraint_terms(P, theta, n, ld, layout);
+    out[n] = logl;
+}
+
+// ---------------------------------------------------------------------------------
+// K2: model positions of one source (positions.py:13-30), one thread per (sample, epoch)
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+stn_model_kernel(const ProbDev P, const int source, const double* __restrict__ theta, const int64_t N,
+                 const int64_t ld, const int layout, const int mode, double* __restrict__ radec,
+                 double* __restrict__ off_mas) {
+    const SrcDev& S = P.src[source];
+    const int E = S.n_epochs;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * E) return;
+    const int64_t n = idx / E;
+    const int e = (int)(idx - n * E);
+    const Params p = load_params(S, theta, n, ld, layout);
+    double m_ra, m_dec, o_ra, o_dec;
+    if (mode == STN_MODE_STRICT) {
+        const StrictTrig t = strict_trig(S, p);
+        strict_offsets(S, p, t, S.strict_rows + (int64_t)e * STN_STRICT_ROW, o_ra, o_dec);
+        m_ra = __dadd_rn(p.ra, __dmul_rn(o_ra, STN_MAS2RAD));
+        m_dec = __dadd_rn(p.dec, __dmul_rn(o_dec, STN_MAS2RAD));
+    } else {
+        const Coef c = make_coef(S, p);
+        const double2* row = reinterpret_cast<const double2*>(S.fast_rows + (int64_t)e * STN_FAST_ROW);
+        double ok_ra, ok_dec;
+        fast_offsets<true>(c, row[0], row[1], row[5], ok_ra, ok_dec);
+        m_ra = c.ra + ok_ra;
+        m_dec = c.dec + ok_dec;
+        o_ra = ok_ra / STN_MAS2RAD;
+        o_dec = ok_dec / STN_MAS2RAD;
+    }
+    double* rd = radec + n * (2 * (int64_t)E);
+    rd[e] = m_ra;
+    rd[E + e] = m_dec;
+    if (off_mas != nullptr) {
+        double* om = off_mas + n * (2 * (int64_t)E);
+        om[e] = o_ra;
+        om[E + e] = o_dec;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// K4: FP64 pipe peak: 8 independent DFMA chains per thread, no memory traffic
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stn_dfma_peak_kernel(double* sink, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-9, x1 = x0 + 1.0, x2 = x0 + 2.0, x3 = x0 + 3.0;
+    double x4 = x0 + 4.0, x5 = x0 + 5.0, x6 = x0 + 6.0, x7 = x0 + 7.0;
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123.456) sink[0] = s;   // never true in practice; keeps the chains alive
+}
+
+// ---------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define STN_CUDA(call)                                                                        \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(STN_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                  \
+    } while (0)
+
+}  // namespace
+
+struct StnCtx {
+    int device = 0;
+    int sm_count = 0;
+    ProbDev prob{};
+    std::vector<void*> dev_allocs;
+    std::vector<int> n_epochs;          // per source
+    int max_epochs = 0;
+    int64_t launches = 0;
+    // *_host staging
+    cudaStream_t streams[2] = {nullptr, nullptr};
+    cudaStream_t timing_stream = nullptr;
+    double* stage_theta[2] = {nullptr, nullptr};
+    double* stage_out[2] = {nullptr, nullptr};
+    int64_t stage_rows = 0;
+};
+
+namespace {
+
+template <typename T>
+int upload(StnCtx* ctx, const T* host, size_t count, const T** dev_out) {
+    void* d = nullptr;
+    const size_t bytes = (count ? count : 1) * sizeof(T);
+    STN_CUDA(cudaMalloc(&d, bytes));
+    ctx->dev_allocs.push_back(d);
+    if (count) STN_CUDA(cudaMemcpy(d, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    *dev_out = static_cast<const T*>(d);
+    return STN_OK;
+}
+
+int pick_lanes(const StnCtx* ctx, int64_t n) {
+    // enough threads for ~2 CTAs on every SM; never more lanes than a quarter of the
+    // longest epoch list (the prologue is replicated on every lane)
+    const int64_t target = (int64_t)2 * ctx->sm_count * kThreads;
+    int cap = 1;
+    while (cap < 32 && cap * 8 <= ctx->max_epochs) cap *= 2;
+    int L = 1;
+    while (L < cap && n * L < target) L *= 2;
+    return L;
+}
+
+template <int R, int L>
+int launch_fast(StnCtx* ctx, const double* theta, int64_t n, int64_t ld, int layout, double* out,
+                cudaStream_t st) {
+    constexpr int per_cta = (kThreads / L) * R;
+    const int64_t grid = (n + per_cta - 1) / per_cta;
+    if (grid > 0x7fffffffLL) return fail(STN_ERR_INVALID, "batch too large for one launch");
+    stn_loglike_fast_kernel<R, L><<<(unsigned)grid, kThreads, 0, st>>>(ctx->prob, theta, n, ld, layout, out);
+    STN_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return STN_OK;
+}
+
+int launch_loglike(StnCtx* ctx, const double* theta, int64_t n, int64_t ld, int layout, int mode,
+                   int lanes, double* out, cudaStream_t st) {
+    if (n == 0) return STN_OK;
+    if (mode == STN_MODE_STRICT) {
+        const int64_t grid = (n + kThreads - 1) / kThreads;
+        stn_loglike_strict_kernel<<<(unsigned)grid, kThreads, 0, st>>>(ctx->prob, theta, n, ld, layout, out);
+        STN_CUDA(cudaGetLastError());
+        ctx->launches++;
+        return STN_OK;
+    }
+    if (lanes == 0) lanes = pick_lanes(ctx, n);
+    switch (lanes) {
+        case 1:
+            // R only changes how samples map to threads, never a result bit
+            if (n >= (int64_t)4 * ctx->sm_count * kThreads)
+                return launch_fast<2, 1>(ctx, theta, n, ld, layout, out, st);
+            return launch_fast<1, 1>(ctx, theta, n, ld, layout, out, st);
+        case 2: return launch_fast<1, 2>(ctx, theta, n, ld, layout, out, st);
+        case 4: return launch_fast<1, 4>(ctx, theta, n, ld, layout, out, st);
+        case 8: return launch_fast<1, 8>(ctx, theta, n, ld, layout, out, st);
+        case 16: return launch_fast<1, 16>(ctx, theta, n, ld, layout, out, st);
+        case 32: return launch_fast<1, 32>(ctx, theta, n, ld, layout, out, st);
+        default: return fail(STN_ERR_INVALID, "lanes must be 0 or a power of two <= 32 (got %d)", lanes);
+    }
+}
+
+int check_call(StnCtx* ctx, const void* theta, int64_t n, int64_t ld, int layout, int mode,
+               const void* out) {
+    if (!ctx) return fail(STN_ERR_INVALID, "null context");
+    if (n < 0) return fail(STN_ERR_INVALID, "negative batch size");
+    if (n > 0 && (!theta || !out)) return fail(STN_ERR_INVALID, "null buffer");
+    if (layout != STN_LAYOUT_AOS && layout != STN_LAYOUT_SOA) return fail(STN_ERR_INVALID, "bad layout %d", layout);
+    if (mode != STN_MODE_FAST && mode != STN_MODE_STRICT) return fail(STN_ERR_INVALID, "bad mode %d", mode);
+    if (layout == STN_LAYOUT_AOS && ld < ctx->prob.n_params)
+        return fail(STN_ERR_INVALID, "AoS leading dimension %lld < P = %d", (long long)ld, ctx->prob.n_params);
+    if (layout == STN_LAYOUT_SOA && ld < n)
+        return fail(STN_ERR_INVALID, "SoA leading dimension %lld < n = %lld", (long long)ld, (long long)n);
+    return STN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int stn_version(void) { return STN_ABI_VERSION; }
+
+const char* stn_last_error(void) { return g_err.c_str(); }
+
+int stn_create(const StnProblem* pb, int device, StnCtx** out_ctx) {
+    if (!pb || !out_ctx) return fail(STN_ERR_INVALID, "null argument");
+    *out_ctx = nullptr;
+    if (pb->n_sources <= 0 || !pb->sources) return fail(STN_ERR_INVALID, "problem has no sources");
+    if (pb->n_params <= 0) return fail(STN_ERR_INVALID, "problem has no parameters");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(STN_ERR_DEVICE, "no CUDA device visible (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(STN_ERR_INVALID, "device %d out of range (%d visible)", device, ndev);
+    cudaDeviceProp prop;
+    STN_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(STN_ERR_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    STN_CUDA(cudaSetDevice(device));
+
+    StnCtx* ctx = new (std::nothrow) StnCtx();
+    if (!ctx) return fail(STN_ERR_NOMEM, "out of host memory");
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+
+    auto bail = [&](int code) {
+        stn_destroy(ctx);
+        return code;
+    };
+
+    std::vector<SrcDev> src(pb->n_sources);
+    std::vector<ChunkDev> chunks;
+    for (int s = 0; s < pb->n_sources; ++s) {
+        const StnSource& hs = pb->sources[s];
+        if (hs.n_epochs < 0 || hs.n_epochs > 0x3fffffff) return bail(fail(STN_ERR_INVALID, "source %d: bad epoch count", s));
+        if (hs.n_epochs > 0 && (!hs.fast_rows || !hs.strict_rows))
+            return bail(fail(STN_ERR_INVALID, "source %d: null epoch table", s));
+        for (int r = 0; r < STN_NROOTS; ++r)
+            if (hs.col[r] >= pb->n_params)
+                return bail(fail(STN_ERR_INVALID, "source %d: column %d out of range (P = %d)", s, hs.col[r], pb->n_params));
+        if (hs.efac_on && hs.col[STN_EFAC] < 0)
+            return bail(fail(STN_ERR_INVALID, "source %d: efac_on without an efac column", s));
+        SrcDev& d = src[s];
+        std::memset(&d, 0, sizeof(d));
+        int rc = upload(ctx, hs.fast_rows, (size_t)hs.n_epochs * STN_FAST_ROW, &d.fast_rows);
+        if (rc) return bail(rc);
+        rc = upload(ctx, hs.strict_rows, (size_t)hs.n_epochs * STN_STRICT_ROW, &d.strict_rows);
+        if (rc) return bail(rc);
+        d.n_epochs = (int)hs.n_epochs;
+        for (int r = 0; r < STN_NROOTS; ++r) d.col[r] = hs.col[r];
+        d.efac_on = hs.efac_on ? 1 : 0;
+        d.binary = hs.binary ? 1 : 0;
+        d.cos_decj = hs.binary ? hs.cos_decj : 1.0;
+        d.inv_cos_decj = 1.0 / d.cos_decj;
+        d.neg_sum_log_err = hs.neg_sum_log_err;
+        d.a1_lts = hs.a1_lts;
+        ctx->n_epochs.push_back(d.n_epochs);
+        if (d.n_epochs > ctx->max_epochs) ctx->max_epochs = d.n_epochs;
+        // chunk list: every source contributes at least one (possibly empty) chunk so that
+        // its prologue / fold always runs
+        int done = 0;
+        do {
+            ChunkDev c;
+            c.rows = d.fast_rows + (size_t)done * STN_FAST_ROW;
+            c.n_epochs = (d.n_epochs - done) < kChunk ? (d.n_epochs - done) : kChunk;
+            c.source = s;
+            c.flags = (done == 0 ? kFirst : 0);
+            c.pad = 0;
+            done += c.n_epochs;
+            if (done >= d.n_epochs) c.flags |= kLast;
+            chunks.push_back(c);
+        } while (done < d.n_epochs);
+    }
+    for (int k = 0; k < pb->n_a1dot; ++k)
+        if (pb->a1dot_source[k] < 0 || pb->a1dot_source[k] >= pb->n_sources)
+            return bail(fail(STN_ERR_INVALID, "a1dot constraint %d: bad source", k));
+    for (int k = 0; k < pb->n_sini; ++k)
+        if (pb->sini_col[k] < 0 || pb->sini_col[k] >= pb->n_params)
+            return bail(fail(STN_ERR_INVALID, "sin(incl) constraint %d: bad column", k));
+
+    ProbDev& P = ctx->prob;
+    P.n_sources = pb->n_sources;
+    P.n_params = pb->n_params;
+    P.n_chunks = (int)chunks.size();
+    P.n_a1dot = pb->n_a1dot;
+    P.n_sini = pb->n_sini;
+    int rc;
+    if ((rc = upload(ctx, src.data(), src.size(), &P.src))) return bail(rc);
+    if ((rc = upload(ctx, chunks.data(), chunks.size(), &P.chunks))) return bail(rc);
+    if ((rc = upload(ctx, pb->a1dot_source, (size_t)pb->n_a1dot, &P.a1_src))) return bail(rc);
+    if ((rc = upload(ctx, pb->a1dot_mu, (size_t)pb->n_a1dot, &P.a1_mu))) return bail(rc);
+    if ((rc = upload(ctx, pb->a1dot_sigma, (size_t)pb->n_a1dot, &P.a1_sigma))) return bail(rc);
+    if ((rc = upload(ctx, pb->sini_col, (size_t)pb->n_sini, &P.sini_col))) return bail(rc);
+    if ((rc = upload(ctx, pb->sini_mu, (size_t)pb->n_sini, &P.sini_mu))) return bail(rc);
+    if ((rc = upload(ctx, pb->sini_sigma, (size_t)pb->n_sini, &P.sini_sigma))) return bail(rc);
+    *out_ctx = ctx;
+    return STN_OK;
+}
+
+int stn_destroy(StnCtx* ctx) {
+    if (!ctx) return STN_OK;
+    cudaSetDevice(ctx->device);
+    for (void* p : ctx->dev_allocs) cudaFree(p);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->stage_theta[i]) cudaFree(ctx->stage_theta[i]);
+        if (ctx->stage_out[i]) cudaFree(ctx->stage_out[i]);
+        if (ctx->streams[i]) cudaStreamDestroy(ctx->streams[i]);
+    }
+    if (ctx->timing_stream) cudaStreamDestroy(ctx->timing_stream);
+    delete ctx;
+    return STN_OK;
+}
+
+int stn_auto_lanes(StnCtx* ctx, int64_t n) {
+    if (!ctx) return fail(STN_ERR_INVALID, "null context");
+    return pick_lanes(ctx, n);
+}
+
+int64_t stn_launch_count(StnCtx* ctx) { return ctx ? ctx->launches : 0; }
+
+int stn_loglike(StnCtx* ctx, const double* theta_dev, int64_t n, int64_t ld, int layout, int mode,
+                int lanes, double* out_dev, void* stream) {
+    int rc = check_call(ctx, theta_dev, n, ld, layout, mode, out_dev);
+    if (rc) return rc;
+    STN_CUDA(cudaSetDevice(ctx->device));
+    return launch_loglike(ctx, theta_dev, n, ld, layout, mode, lanes, out_dev, static_cast<cudaStream_t>(stream));
+}
+
+int stn_loglike_timed(StnCtx* ctx, const double* theta_dev, int64_t n, int64_t ld, int layout,
+                      int mode, int lanes, double* out_dev, int steps, double* total_ms) {
+    int rc = check_call(ctx, theta_dev, n, ld, layout, mode, out_dev);
+    if (rc) return rc;
+    if (steps <= 0 || !total_ms) return fail(STN_ERR_INVALID, "bad steps / null total_ms");
+    STN_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->timing_stream) STN_CUDA(cudaStreamCreateWithFlags(&ctx->timing_stream, cudaStreamNonBlocking));
+    cudaEvent_t e0, e1;
+    STN_CUDA(cudaEventCreate(&e0));
+    STN_CUDA(cudaEventCreate(&e1));
+    STN_CUDA(cudaDeviceSynchronize());
+    STN_CUDA(cudaEventRecord(e0, ctx->timing_stream));
+    for (int i = 0; i < steps; ++i) {
+        rc = launch_loglike(ctx, theta_dev, n, ld, layout, mode, lanes, out_dev, ctx->timing_stream);
+        if (rc) return rc;
+    }
+    STN_CUDA(cudaEventRecord(e1, ctx->timing_stream));
+    STN_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    STN_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *total_ms = ms;
+    return STN_OK;
+}
+
+int stn_loglike_host(StnCtx* ctx, const double* theta_host, int64_t n, int64_t ld, int layout,
+                     int mode, int lanes, double* out_host) {
+    int rc = check_call(ctx, theta_host, n, ld, layout, mode, out_host);
+    if (rc) return rc;
+    if (n == 0) return STN_OK;
+    STN_CUDA(cudaSetDevice(ctx->device));
+    const int P = ctx->prob.n_params;
+    // chunk so that copies of chunk i+1 overlap the kernel of chunk i
+    int64_t rows = n;
+    const int64_t max_rows = (int64_t)1 << 18;
+    if (rows > max_rows) rows = max_rows;
+    if (ctx->stage_rows < rows) {
+        for (int i = 0; i < 2; ++i) {
+            if (ctx->stage_theta[i]) cudaFree(ctx->stage_theta[i]);
+            if (ctx->stage_out[i]) cudaFree(ctx->stage_out[i]);
+            ctx->stage_theta[i] = ctx->stage_out[i] = nullptr;
+        }
+        ctx->stage_rows = 0;
+        for (int i = 0; i < 2; ++i) {
+            STN_CUDA(cudaMalloc(&ctx->stage_theta[i], (size_t)rows * P * sizeof(double)));
+            STN_CUDA(cudaMalloc(&ctx->stage_out[i], (size_t)rows * sizeof(double)));
+        }
+        ctx->stage_rows = rows;
+    }
+    for (int i = 0; i < 2; ++i)
+        if (!ctx->streams[i]) STN_CUDA(cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking));
+    if (mode == STN_MODE_FAST && lanes == 0) lanes = pick_lanes(ctx, n);   // from the whole batch
+    int k = 0;
+    for (int64_t lo = 0; lo < n; lo += rows, ++k) {
+        const int64_t m = (n - lo) < rows ? (n - lo) : rows;
+        cudaStream_t st = ctx->streams[k & 1];
+        double* dth = ctx->stage_theta[k & 1];
+        double* dout = ctx->stage_out[k & 1];
+        int64_t dld;
+        if (layout == STN_LAYOUT_AOS) {
+            // rows are contiguous; keep only the first P columns of each
+            STN_CUDA(cudaMemcpy2DAsync(dth, (size_t)P * sizeof(double), theta_host + lo * ld,
+                                       (size_t)ld * sizeof(double), (size_t)P * sizeof(double), (size_t)m,
+                                       cudaMemcpyHostToDevice, st));
+            dld = P;
+        } else {
+            STN_CUDA(cudaMemcpy2DAsync(dth, (size_t)m * sizeof(double), theta_host + lo,
+                                       (size_t)ld * sizeof(double), (size_t)m * sizeof(double), (size_t)P,
+                                       cudaMemcpyHostToDevice, st));
+            dld = m;
+        }
+        rc = launch_loglike(ctx, dth, m, dld, layout, mode, lanes, dout, st);
+        if (rc) return rc;
+        STN_CUDA(cudaMemcpyAsync(out_host + lo, dout, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    STN_CUDA(cudaStreamSynchronize(ctx->streams[0]));
+    STN_CUDA(cudaStreamSynchronize(ctx->streams[1]));
+    return STN_OK;
+}
+
+int stn_model(StnCtx* ctx, int source, const double* theta_dev, int64_t n, int64_t ld, int layout,
+              int mode, double* radec_dev, double* off_mas_dev, void* stream) {
+    int rc = check_call(ctx, theta_dev, n, ld, layout, mode, radec_dev);
+    if (rc) return rc;
+    if (source < 0 || source >= ctx->prob.n_sources) return fail(STN_ERR_INVALID, "source %d out of range", source);
+    const int64_t total = n * (int64_t)ctx->n_epochs[source];
+    if (total == 0) return STN_OK;
+    STN_CUDA(cudaSetDevice(ctx->device));
+    const int64_t grid = (total + kThreads - 1) / kThreads;
+    if (grid > 0x7fffffffLL) return fail(STN_ERR_INVALID, "batch too large for one launch");
+    stn_model_kernel<<<(unsigned)grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        ctx->prob, source, theta_dev, n, ld, layout, mode, radec_dev, off_mas_dev);
+    STN_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return STN_OK;
+}
+
+int stn_host_alloc(void** ptr, int64_t bytes) {
+    if (!ptr || bytes < 0) return fail(STN_ERR_INVALID, "bad argument");
+    STN_CUDA(cudaHostAlloc(ptr, (size_t)(bytes ? bytes : 1), cudaHostAllocDefault));
+    return STN_OK;
+}
+
+int stn_host_free(void* ptr) {
+    if (ptr) STN_CUDA(cudaFreeHost(ptr));
+    return STN_OK;
+}
+
+int stn_fp64_peak(int device, int iters, int reps, double* tflops, double* ms_out) {
+    if (iters <= 0 || reps <= 0 || !tflops) return fail(STN_ERR_INVALID, "bad argument");
+    STN_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    STN_CUDA(cudaGetDeviceProperties(&prop, device));
+    double* sink = nullptr;
+    STN_CUDA(cudaMalloc(&sink, sizeof(double)));
+    cudaEvent_t e0, e1;
+    STN_CUDA(cudaEventCreate(&e0));
+    STN_CUDA(cudaEventCreate(&e1));
+    const int grid = prop.multiProcessorCount * 8;
+    const int block = 256;
+    double best = 1e300;
+    for (int r = 0; r < reps + 1; ++r) {   // first launch is the warm-up
+        STN_CUDA(cudaEventRecord(e0, 0));
+        stn_dfma_peak_kernel<<<grid, block>>>(sink, iters, 0.999999, 1e-9);
+        STN_CUDA(cudaGetLastError());
+        STN_CUDA(cudaEventRecord(e1, 0));
+        STN_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        STN_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (r > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    const double flops = 2.0 * 8.0 * (double)iters * (double)grid * (double)block;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    return STN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,249 @@
+"""Drop-in `Gaussianlikelihood` and `positions` backed by the sm_100a kernels.
+
+Same class name, constructor arguments, `.parameters` dict and no-argument
+`log_likelihood()` as the reference (simulate.py:325-384), plus the batched entry
+point `log_likelihood_batch(theta)` for vectorised samplers.  `positions(...)` keeps
+the reference signature (positions.py:13).
+"""
+import collections
+import numpy as np
+
+from . import _lib
+from .constants import SENTINEL
+from .problem import CompiledProblem, DeviceContext
+from .shares import filter_dictionary_of_parameter_with_index
+
+try:                                            # bilby is optional: samplers need it, the math does not
+    from bilby import Likelihood as _LikelihoodBase
+except Exception:                               # pragma: no cover - bilby absent in this image
+    class _LikelihoodBase(object):
+        """Minimal stand-in with bilby.Likelihood's attributes."""
+
+        def __init__(self, parameters=None):
+            self.parameters = parameters if parameters is not None else {}
+            self._meta_data = None
+
+        def log_likelihood(self):
+            raise NotImplementedError
+
+        def noise_log_likelihood(self):
+            return np.nan
+
+        def log_likelihood_ratio(self):
+            return self.log_likelihood() - self.noise_log_likelihood()
+
+
+_default_earth_provider = None
+
+
+def set_default_earth_provider(provider):
+    """Earth-ephemeris provider used when none is passed explicitly (ephemeris.py)."""
+    global _default_earth_provider
+    _default_earth_provider = provider
+
+
+def _resolve_provider(provider):
+    if provider is not None:
+        return provider
+    if _default_earth_provider is not None:
+        return _default_earth_provider
+    from .ephemeris import default_provider
+    return default_provider()
+
+
+def _is_torch_tensor(x):
+    return type(x).__module__.startswith('torch') and hasattr(x, 'data_ptr')
+
+
+class Gaussianlikelihood(_LikelihoodBase):
+    """Sum over sources of -1/2 sum((obs - model)/sigma)^2 - sum(log sigma), plus the
+    optional a1dot and sin(incl) Gaussian terms (simulate.py:362-384), evaluated on a B200.
+
+    Positional arguments are the reference's (simulate.py:326).  `positions` is accepted
+    for signature compatibility and ignored: the model is the device kernel.
+    Keyword-only extras: earth_provider / earth_xyz (ephemeris.py), device, mode
+    ('fast' | 'strict'), lanes (0 = automatic).
+    """
+
+    def __init__(self, refepoch, list_of_dict_timing, list_of_dict_VLBI, shares, positions=None,
+                 DoD_additional_constraints=None, a1dot_constraints=False, *, earth_provider=None,
+                 earth_xyz=None, device=0, mode='fast', lanes=0):
+        self.refepoch = refepoch
+        self.LoD_VLBI = list_of_dict_VLBI
+        self.LoD_timing = list_of_dict_timing
+        self.positions = positions
+        self.shares = shares
+        self.number_of_pmparins = len(self.LoD_VLBI)
+        if DoD_additional_constraints is None:
+            DoD_additional_constraints = {'sin_incl_Gaussian_constraints': {}, 'sin_incl_limits_constraints': {}}
+        self.DoD_additional_constraints = DoD_additional_constraints
+        self.dict_sin_incl_Gaussian_constraints = DoD_additional_constraints['sin_incl_Gaussian_constraints']
+        self.a1dot_constraints = a1dot_constraints
+        self.device = int(device)
+        self.mode = _lib.MODES[mode]
+        self.lanes = int(lanes)
+        needs_px = any(int(v) >= 0 for v in shares[7])
+        self._provider = _resolve_provider(earth_provider) if (needs_px and earth_xyz is None) else earth_provider
+        self._earth_xyz = earth_xyz
+        self._contexts = {}
+        ctx = self._context(None)
+        super().__init__(dict.fromkeys(ctx.problem.default_names))
+
+    # ------------------------------------------------------------------ contexts
+    def _context(self, keys):
+        """Device context whose column order is `keys` (default: shares order).  Samplers
+        order columns by their prior keys (.inits line order), hence the cache."""
+        k = None if keys is None else tuple(keys)
+        ctx = self._contexts.get(k)
+        if ctx is None:
+            problem = CompiledProblem(self.refepoch, self.LoD_timing, self.LoD_VLBI, self.shares,
+                                      earth_provider=self._provider,
+                                      DoD_additional_constraints=self.DoD_additional_constraints,
+                                      a1dot_constraints=self.a1dot_constraints, names=keys,
+                                      earth_xyz=self._earth_xyz)
+            if self._earth_xyz is None:
+                self._earth_xyz = [src['earth_xyz'] for src in problem.sources]   # evaluate the ephemeris once
+            ctx = DeviceContext(problem, self.device)
+            self._contexts[k] = ctx
+            if k is None:
+                self._contexts[tuple(problem.default_names)] = ctx
+        return ctx
+
+    @property
+    def parameter_names(self):
+        return list(self._context(None).problem.default_names)
+
+    @property
+    def evals_per_sample(self):
+        return self._context(None).problem.evals_per_sample
+
+    # ------------------------------------------------------------ reference API
+    def log_likelihood(self):
+        """simulate.py:362: one parameter vector taken from self.parameters."""
+        names = self.parameter_names
+        theta = np.array([[float(self.parameters[k]) for k in names]], dtype=np.float64)
+        return float(self.log_likelihood_batch(theta)[0])
+
+    # ------------------------------------------------------------- batched API
+    def log_likelihood_batch(self, theta, keys=None, out=None, layout='aos', mode=None, lanes=None):
+        """log-L of N parameter vectors.
+
+        theta : (N, P) float64, numpy array or CUDA torch tensor (layout='aos'), or
+                (P, N) with layout='soa'.  Columns follow list(self.parameters) unless
+                `keys` names them.  Returns (N,) of the same kind (numpy / torch).
+        """
+        ctx = self._context(keys)
+        P = ctx.problem.n_params
+        mode = self.mode if mode is None else _lib.MODES[mode]
+        lanes = self.lanes if lanes is None else int(lanes)
+        lay = _lib.LAYOUT_AOS if layout == 'aos' else _lib.LAYOUT_SOA
+        if _is_torch_tensor(theta):
+            import torch
+            if not theta.is_cuda:
+                return torch.from_numpy(self.log_likelihood_batch(theta.numpy(), keys, None, layout, mode, lanes))
+            if theta.dtype != torch.float64 or theta.dim() != 2:
+                raise TypeError('theta must be a 2-D float64 tensor')
+            if theta.device.index != self.device:
+                raise ValueError('theta lives on cuda:%s but this likelihood was built for cuda:%d'
+                                 % (theta.device.index, self.device))
+            if theta.stride(1) != 1:
+                theta = theta.contiguous()
+            n, ld = self._shape(theta.shape, theta.stride(0), lay, P)
+            if out is None:
+                out = torch.empty(n, dtype=torch.float64, device=theta.device)
+            stream = torch.cuda.current_stream(theta.device).cuda_stream
+            ctx.loglike_ptr(theta.data_ptr(), n, ld, lay, mode, lanes, out.data_ptr(), stream)
+            return out
+        theta = np.asarray(theta, dtype=np.float64)
+        if theta.ndim != 2:
+            raise TypeError('theta must be 2-D')
+        if theta.strides[1] != 8 or theta.strides[0] % 8 != 0 or theta.strides[0] < 0:
+            theta = np.ascontiguousarray(theta)
+        n, ld = self._shape(theta.shape, theta.strides[0] // 8, lay, P)
+        if out is None:
+            out = np.empty(n, dtype=np.float64)
+        ctx.loglike_host_ptr(theta.ctypes.data, n, ld, lay, mode, lanes, out.ctypes.data)
+        return out
+
+    @staticmethod
+    def _shape(shape, stride0, lay, P):
+        if lay == _lib.LAYOUT_AOS:
+            if shape[1] != P:
+                raise ValueError('theta has %d columns, the model has %d parameters' % (shape[1], P))
+            return int(shape[0]), int(stride0) if shape[0] > 1 else max(int(stride0), P)
+        if shape[0] != P:
+            raise ValueError('theta has %d rows, the model has %d parameters' % (shape[0], P))
+        return int(shape[1]), int(stride0) if shape[0] > 1 else max(int(stride0), int(shape[1]))
+
+    def model_positions(self, theta, source, keys=None, mode=None, offsets=False):
+        """Model RA/Dec of one source for N parameter vectors: (N, 2E) = [ra..., dec...] rad
+        (positions.py:13-30); with offsets=True also the (N, 2E) offsets in mas."""
+        import torch
+        ctx = self._context(keys)
+        mode = self.mode if mode is None else _lib.MODES[mode]
+        dev = torch.device('cuda', self.device)
+        was_numpy = not _is_torch_tensor(theta)
+        th = torch.as_tensor(np.asarray(theta, dtype=np.float64) if was_numpy else theta)
+        th = th.to(dev, torch.float64).contiguous()
+        n, P = th.shape
+        if P != ctx.problem.n_params:
+            raise ValueError('theta has %d columns, the model has %d parameters' % (P, ctx.problem.n_params))
+        E = ctx.problem.sources[source]['n_epochs']
+        radec = torch.empty((n, 2 * E), dtype=torch.float64, device=dev)
+        off = torch.empty((n, 2 * E), dtype=torch.float64, device=dev) if offsets else None
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        ctx.model_ptr(source, th.data_ptr(), n, P, _lib.LAYOUT_AOS, mode, radec.data_ptr(),
+                      off.data_ptr() if offsets else None, stream)
+        if was_numpy:
+            radec = radec.cpu().numpy()
+            off = off.cpu().numpy() if offsets else None
+        return (radec, off) if offsets else radec
+
+    def close(self):
+        seen = set()
+        for ctx in self._contexts.values():
+            if id(ctx) not in seen:
+                seen.add(id(ctx))
+                ctx.close()
+        self._contexts = {}
+
+
+# ------------------------------------------------------------------------------------
+# positions(): the reference's stateless model function (positions.py:13-30)
+# ------------------------------------------------------------------------------------
+_positions_cache = collections.OrderedDict()
+_POSITIONS_CACHE_SIZE = 16
+
+
+def positions(refepoch, epochs, dict_timing, parameter_filter_index, dict_parameters, *,
+              earth_provider=None, device=0, mode='strict'):
+    """Model positions [ra(E)..., dec(E)...] in rad for one source.  The parameters of
+    source `parameter_filter_index` are picked from `dict_parameters` exactly as the
+    reference does (missing roots = -999).  Device contexts are cached per
+    (refepoch, epochs, parfile) so repeated calls only launch the model kernel."""
+    epochs = np.ascontiguousarray(epochs, dtype=np.float64)
+    FP = filter_dictionary_of_parameter_with_index(dict_parameters, parameter_filter_index)
+    keys = sorted(FP.keys())
+    vals = [float(FP[k]) for k in keys]          # dec, efac, efad, incl, mu_a, mu_d, om_asc, px, ra
+    present = [v != SENTINEL for v in vals]
+    tkey = tuple(sorted((k, v) for k, v in dict_timing.items())) if dict_timing != {} else ()
+    key = (float(refepoch), epochs.tobytes(), tkey, tuple(present), int(device), id(earth_provider))
+    like = _positions_cache.get(key)
+    if like is None:
+        E = epochs.shape[0]
+        shares = [[0] if on else [-1] for on in present]
+        shares[1], shares[2] = [-1], [-1]        # EFAC plays no role in the model
+        vlbi = {'epochs': epochs, 'radecs': np.zeros(2 * E), 'errs': np.ones(2 * E)}
+        like = Gaussianlikelihood(refepoch, [dict_timing], [vlbi], shares, None, None,
+                                  earth_provider=earth_provider, device=device, mode=mode)
+        _positions_cache[key] = like
+        while len(_positions_cache) > _POSITIONS_CACHE_SIZE:
+            _positions_cache.popitem(last=False)[1].close()
+    else:
+        _positions_cache.move_to_end(key)
+    theta = np.array([[dict(zip(keys, vals))[_root_of(n)] for n in like.parameter_names]], dtype=np.float64)
+    return like.model_positions(theta, 0, mode=mode)[0]
+
+
+def _root_of(name):
+    return '_'.join(t for t in name.split('_') if not t.isdigit())
