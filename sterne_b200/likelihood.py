@@ -241,7 +241,8 @@ def positions(refepoch, epochs, dict_timing, parameter_filter_index, dict_parame
             _positions_cache.popitem(last=False)[1].close()
     else:
         _positions_cache.move_to_end(key)
-    theta = np.array([[dict(zip(keys, vals))[_root_of(n)] for n in like.parameter_names]], dtype=np.float64)
+    by_root = {_root_of(k): v for k, v in zip(keys, vals)}
+    theta = np.array([[by_root[_root_of(n)] for n in like.parameter_names]], dtype=np.float64)
     return like.model_positions(theta, 0, mode=mode)[0]
 
 

@@ -1,0 +1,167 @@
+"""CPU-side tests of the product's host logic (no GPU): readers, parameter naming and
+routing, orbit precompute, problem compiler, and the C-ABI library's exported symbols."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import sterne_b200 as sb
+from sterne_b200 import _lib, orbit, problem, shares as sh, synthetic
+from oracle import sterne_oracle as O
+from conftest import ROOT
+
+
+def test_readers_match_reference(golden, golden_dir):
+    for case in golden['cases']:
+        f = golden_dir[case['name']]
+        VLBI = sb.create_list_of_dict_VLBI(f['pmparins'], f['preliminaries'])
+        timing = sb.create_list_of_dict_timing(f['parfiles'])
+        limits, DoD = sb.read_inits(f['inits'])
+        for mine, ref in zip(VLBI, case['ref']['VLBI']):
+            assert set(mine) == set(ref)
+            for k in ref:
+                assert np.array_equal(mine[k], np.array(ref[k])), (case['name'], k)
+        for mine, ref in zip(timing, case['ref']['timing']):
+            assert mine == ref, case['name']
+        assert limits == case['ref']['limits'] and DoD == case['ref']['DoD']
+
+
+def test_dms_decyear_names(golden):
+    for item in golden['dms2deg']:
+        assert sb.dms2deg(item['s']) == item['deg']
+    for item in golden['decyear2mjd']:
+        assert sb.decyear2mjd(item['epoch']) == item['mjd']
+    for item in golden['shares_names']:
+        assert list(sb.get_parameters_from_shares(item['shares'])) == item['names']
+
+
+def test_reader_error_behaviour(tmp_path):
+    p = tmp_path / 'x.pmpar.in'
+    p.write_text('57000.0 12:00:00.0  0.0001 30:00:00.0 0.001\n')      # double space: reference raises too
+    with pytest.raises(ValueError):
+        sb.readpmparin(str(p))
+    q = tmp_path / 'x.par'
+    q.write_text('PB              1.5\nECC             0.1\n')
+    with pytest.raises(KeyError):
+        sb.read_parfile(str(q))
+    with pytest.raises(ValueError):
+        sb.get_parameters_from_shares([[0]] * 8)
+
+
+def test_column_table_equals_reference_routing(golden):
+    """column_table() == filter_dictionary_of_parameter_with_index + sorted positional pick."""
+    for item in golden['shares_names']:
+        names = item['names']
+        S = len(item['shares'][0])
+        idx = sh.column_table(names, S)
+        values = {k: float(i + 1) for i, k in enumerate(names)}
+        for s in range(S):
+            FP = O.filter_dictionary_of_parameter_with_index(values, s)
+            Ps = sorted(FP.keys())
+            for r in range(9):
+                want = FP[Ps[r]]
+                got = -999 if idx[s, r] < 0 else values[names[idx[s, r]]]
+                assert got == want, (names, s, r)
+            mine = sh.filter_dictionary_of_parameter_with_index(values, s)
+            assert mine == FP
+
+
+def test_orbit_terms_equal_oracle():
+    for variant in ('plain', 'wide', 'dots'):
+        case = synthetic.config3(variant)
+        t = case.LoD_timing[0]
+        ep = case.LoD_VLBI[0]['epochs']
+        got = orbit.orbit_terms(ep, t)
+        for i, e in enumerate(ep):
+            want = O.reflex_orbit_terms(e, t)
+            assert tuple(got[i]) == tuple(float(w) for w in want)
+    assert orbit.solve_u(0.3, 500.123) == O.solve_u(0.3, 500.123)
+
+
+def test_problem_compiler_tables():
+    case = synthetic.config4()
+    pb = problem.CompiledProblem(case.refepoch, case.LoD_timing, case.LoD_VLBI, case.shares,
+                                 earth_xyz=case.earth_xyz)
+    assert pb.n_params == 16 and pb.n_sources == 5
+    assert pb.evals_per_sample == sum(10 + s for s in range(5))
+    for s, src in enumerate(pb.sources):
+        E = src['n_epochs']
+        v = case.LoD_VLBI[s]
+        assert src['efac_on'] and src['binary']
+        assert np.array_equal(src['fast'][:, 4], v['radecs'][:E])
+        assert np.array_equal(src['fast'][:, 6], v['errs_random'][:E] ** 2)
+        assert np.array_equal(src['strict'][:, 11], v['errs_sys'][E:])
+        assert np.array_equal(src['fast'][:, 1:4], case.earth_xyz[s])
+    # column permutation through `keys`
+    keys = list(reversed(pb.names))
+    pb2 = problem.CompiledProblem(case.refepoch, case.LoD_timing, case.LoD_VLBI, case.shares,
+                                  earth_xyz=case.earth_xyz, names=keys)
+    assert all(keys[pb2.idx[s, r]] == pb.names[pb.idx[s, r]] for s in range(5) for r in range(9) if pb.idx[s, r] >= 0)
+    with pytest.raises(ValueError):
+        problem.CompiledProblem(case.refepoch, case.LoD_timing, case.LoD_VLBI, case.shares,
+                                earth_xyz=case.earth_xyz, names=keys[:-1])
+    # EFAC requested but no .preliminary errors: KeyError as in simulate.py:317
+    v = [{k: d[k] for k in ('epochs', 'radecs', 'errs')} for d in case.LoD_VLBI]
+    with pytest.raises(KeyError):
+        problem.CompiledProblem(case.refepoch, case.LoD_timing, v, case.shares, earth_xyz=case.earth_xyz)
+
+
+def test_a1dot_broadcast_rules():
+    case = synthetic.config4()
+    mk = lambda a: problem.CompiledProblem(case.refepoch, case.LoD_timing, case.LoD_VLBI, case.shares,
+                                           earth_xyz=case.earth_xyz, a1dot_constraints=a)
+    p = mk([[1e-14, 2e-15], [], [], [], []])
+    assert list(p.a1_source) == [0, 1, 2, 3, 4] and list(p.a1_mu) == [1e-14] * 5     # (5,) - (1,)
+    p = mk([[1e-14, 2e-15]] * 5)
+    assert list(p.a1_source) == [0, 1, 2, 3, 4]
+    with pytest.raises(ValueError):
+        mk([[1e-14, 2e-15], [1e-14, 2e-15], [], [], []])                             # (5,) - (2,)
+    assert len(mk([[], [], [], [], []]).a1_source) == 0
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, 'include', 'sterne_b200.h')).read()
+    declared = set(re.findall(r'\b(stn_[a-z0-9_]+)\s*\(', header))
+    assert declared, 'no declarations found'
+    lib = _lib.load()
+    assert declared == {name for name, _, _ in _lib.SYMBOLS}
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.stn_version() == 1
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    case = synthetic.config1()
+    with pytest.raises(_lib.StnError) as err:
+        case.likelihood()
+    assert 'no CPU path' in str(err.value) or 'CUDA' in str(err.value)
+
+
+def test_analytic_earth_orbit_is_sane():
+    prov = sb.AnalyticEarthProvider()
+    jd = 2451545.0 + np.linspace(0, 3652, 500)
+    xyz = prov(jd)
+    r = np.linalg.norm(xyz, axis=1)
+    assert r.min() > 0.98 and r.max() < 1.02
+    # obliquity: z/y amplitude ratio ~ tan(23.44 deg)
+    assert abs(np.abs(xyz[:, 2]).max() / np.abs(xyz[:, 1]).max() - np.tan(np.radians(23.43928))) < 5e-3
+    # around the March equinox the Earth is near -x (Sun at RA 0 as seen from the Earth)
+    k = np.argmin(np.abs(jd - 2451623.8))
+    assert xyz[k, 0] < -0.98
+
+
+def test_files_round_trip_to_memory_case(tmp_path):
+    case = synthetic.config4()
+    f = synthetic.write_case_files(case, str(tmp_path))
+    VLBI = sb.create_list_of_dict_VLBI(f['pmparins'], f['preliminaries'])
+    for a, b in zip(VLBI, case.LoD_VLBI):
+        assert np.allclose(a['epochs'], b['epochs'], atol=1e-6, rtol=0)
+        assert np.abs(a['radecs'] - b['radecs']).max() < 1e-13         # 1e-10 s of time
+        assert np.allclose(a['errs'], b['errs'], rtol=1e-10)
+    timing = sb.create_list_of_dict_timing(f['parfiles'])
+    assert timing[0]['pb'] == case.LoD_timing[0]['pb'] and timing[0]['a1'] == case.LoD_timing[0]['a1']
