@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py -- log-L evals/s (sample x source x epoch) of the astrometric likelihood.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[4], the one the metric is quoted on): 2^22 parameter
+vectors PER GPU x 8 sources x 1024 epochs, full model (shared parallax / proper motion
+/ EFAC, source 0 a binary with Omega_asc + inclination: "variant C", P = 22).
+One step = one pass of the fused likelihood kernel over the batch (+ the NCCL gather
+of the log-L values when N > 1).  Weak scaling: per-GPU batch fixed.
+
+Prints ONE JSON line on rank 0 (see DESIGN.md "Measurement" for every key).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'log-L evals/sec (sample x source x epoch)'
+UNIT = 'evals/s'
+FLOPS_PER_EVAL = {'A': 30.0, 'B': 42.0, 'C': 43.5}      # algorithmic FP64 flops, SURVEY.md 8(d)
+LOG2_N = 22
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+             'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.QUERY,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.lines:
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': max(smax), 'reasons': sorted(reasons),
+                'samples': len(sm), 'power_w_max': max(power)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(path) as f:
+            return json.load(f), 'measured'
+    except Exception:
+        return {'hbm_gbs': 6650.0}, 'fallback'
+
+
+# --------------------------------------------------------------------------------------
+# reference arm: the CPU restatement of the reference's algorithm on all host cores
+# --------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    if rank != 0:
+        return 0
+    from oracle import cpu_bench                      # the one place bench.py executes oracle/
+    cores = os.cpu_count() or 1
+    rows = args.cpu_rows
+    for _ in range(args.warmup and 1):
+        cpu_bench.time_vectorised('C', rows_per_core=16, cores=cores)
+    vals, walls = [], []
+    for _ in range(args.steps):
+        v, w, c = cpu_bench.time_vectorised('C', rows_per_core=rows, cores=cores)
+        vals.append(v)
+        walls.append(w)
+    total_evals = args.steps * cores * rows * 8 * 1024
+    value = total_evals / sum(walls)
+    sample = ('%d rows/core x %d cores x 8 sources x 1024 epochs per step (of the 2^%d-row workload), '
+              'numpy-vectorised restatement of simulate.py:362-384, one process per core'
+              % (rows, cores, LOG2_N))
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * sum(walls) / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': workload_config(args.gpus),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+        'note': 'dingswin/sterne itself cannot be installed here (astropy, bilby, novas/DE421 absent, no '
+                'network); this is the oracle port of its algorithm, not a measurement of sterne.',
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(n_gpus):
+    return {'workload': 'config5-C: 2^%d parameter vectors per GPU x 8 sources x 1024 epochs, P=22 '
+                        '(shared px, mu_a, mu_d, efac; source 0 binary with incl, om_asc)' % LOG2_N,
+            'samples_per_gpu': 1 << LOG2_N, 'sources': 8, 'epochs_per_source': 1024, 'params': 22,
+            'parallelism': 'dp%d (sample batch sharded, epoch tables replicated)' % n_gpus,
+            'l2': 'theta is 738 MB per GPU, larger than the 126 MB L2: no flush needed between steps',
+            'kernel_mode': 'fast'}
+
+
+# --------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from sterne_b200 import synthetic, fp64_peak
+    from sterne_b200.sharding import ShardedLikelihood
+
+    # CPU baseline first (rank 0, N = 1 only), before this process touches CUDA
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import cpu_bench                  # cpu_baseline leg: checker timed, never shipped
+        cores = os.cpu_count() or 1
+        v, w, c = cpu_bench.time_vectorised('C', rows_per_core=args.cpu_rows, cores=cores)
+        sv, sw = cpu_bench.time_scalar('C', rows=2)
+        cpu_baseline = {
+            'value': v, 'unit': UNIT, 'cores': c, 'kind': 'port',
+            'sample': '%d rows/core x %d cores of the same 8-source x 1024-epoch problem (%.1f s); '
+                      'numpy-vectorised restatement, one process per core' % (args.cpu_rows, c, w),
+            'scalar_value': sv, 'scalar_cores': 1,
+            'scalar_sample': '2 rows through the reference-shaped per-vector Python loop (%.1f s)' % sw}
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; sterne_b200 has no CPU path')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    N = 1 << LOG2_N
+    case = synthetic.config5('C')
+    like = case.likelihood(device=local_rank)
+    ctx = like._context(None)
+    evals_per_step_rank = N * case.evals_per_sample
+    theta = synthetic.device_theta(case, N, seed=1234 + rank, device=dev)
+    out = torch.empty(N, dtype=torch.float64, device=dev)
+    sharded = ShardedLikelihood(like) if world > 1 else None
+    gathered = torch.empty(N * world, dtype=torch.float64, device=dev) if world > 1 else None
+    lanes = ctx.auto_lanes(N * world)
+
+    def step():
+        like.log_likelihood_batch(theta, out=out, lanes=lanes)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    peak_tf, _ = fp64_peak(local_rank, iters=1 << 15, reps=5)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_events = []
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        like.log_likelihood_batch(theta, out=out, lanes=lanes)
+        k1.record()
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)
+        kernel_events.append((k0, k1))
+    e1.record()
+    sync_all()
+    ms_total = e0.elapsed_time(e1)
+    kernel_ms = sum(a.elapsed_time(b) for a, b in kernel_events) / args.steps
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end: host (pinned) buffers through the public API, copies inside the timed region
+    theta_host = torch.empty((N, case.n_params), dtype=torch.float64, pin_memory=True)
+    theta_host.copy_(theta)
+    out_host = torch.empty(N, dtype=torch.float64, pin_memory=True)
+    th_np, out_np = theta_host.numpy(), out_host.numpy()
+    for _ in range(2):
+        like.log_likelihood_batch(th_np, out=out_np, lanes=lanes)
+    sync_all()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        like.log_likelihood_batch(th_np, out=out_np, lanes=lanes)      # synchronous: result is on the host
+    sync_all()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    same = bool(torch.equal(out_host.to(dev), out))
+
+    t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = t.tolist()
+
+    # ---- variants A and B of the same kernel (kernel-only, rank 0, N = 1)
+    variants = {}
+    if world == 1 and not args.no_variants:
+        for vname in ('A', 'B'):
+            vc = synthetic.config5(vname)
+            vl = vc.likelihood(device=local_rank)
+            vt = synthetic.device_theta(vc, N, seed=1234, device=dev)
+            vo = torch.empty(N, dtype=torch.float64, device=dev)
+            for _ in range(3):
+                vl.log_likelihood_batch(vt, out=vo)
+            torch.cuda.synchronize(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(args.steps):
+                vl.log_likelihood_batch(vt, out=vo)
+            b.record()
+            torch.cuda.synchronize(dev)
+            ms = a.elapsed_time(b) / args.steps
+            ev = N * vc.evals_per_sample / (ms * 1e-3)
+            variants[vname] = {'params': vc.n_params, 'ms_per_step': ms, 'evals_per_s': ev,
+                               'fp64_tflops': ev * FLOPS_PER_EVAL[vname] / 1e12,
+                               'fp64_frac': ev * FLOPS_PER_EVAL[vname] / 1e12 / peak_tf}
+            vl.close()
+            del vt, vo
+
+    if rank == 0:
+        peaks, peaks_src = measured_peaks()
+        value = world * evals_per_step_rank * args.steps / (ms_total * 1e-3)
+        k_evals = evals_per_step_rank / (kernel_ms * 1e-3)
+        achieved_tf = k_evals * FLOPS_PER_EVAL['C'] / 1e12
+        alg_bytes = N * (8.0 * case.n_params + 8.0)
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': workload_config(world),
+            'clocks': clocks,
+            'e2e': {'value': world * evals_per_step_rank * e2e_steps / (e2e_ms * 1e-3), 'unit': UNIT,
+                    'h2d_bytes_per_step': world * N * case.n_params * 8, 'd2h_bytes_per_step': world * N * 8,
+                    'ms_per_step': e2e_ms / e2e_steps, 'steps': e2e_steps,
+                    'api': 'Gaussianlikelihood.log_likelihood_batch(numpy pinned) -> stn_loglike_host',
+                    'matches_device_path': same},
+            'gpu_launches': launches,
+            'roofline': {
+                'bound': 'fp64', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
+                'frac': achieved_tf / peak_tf, 'traffic': None,
+                'kernel': 'stn_loglike_fast_kernel<2,1>', 'kernel_ms': kernel_ms,
+                'flops_per_eval': FLOPS_PER_EVAL['C'],
+                'peak_source': 'stn_fp64_peak DFMA micro-benchmark in this run (MEASURED_PEAKS.json has no FP64 '
+                               'figure); nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2',
+                'hbm': {'achieved_gbs': alg_bytes / (kernel_ms * 1e-3) / 1e9, 'peak_gbs': peaks.get('hbm_gbs'),
+                        'peak_source': peaks_src + ' (MEASURED_PEAKS.json)' if peaks_src == 'measured' else 'fallback',
+                        'bytes_per_eval': alg_bytes / evals_per_step_rank},
+            },
+            'cpu_baseline': cpu_baseline,
+            'variants': variants,
+        }
+        print(json.dumps(line))
+    like.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--cpu-rows', type=int, default=4096, help='rows per core of the bounded CPU sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-variants', action='store_true')
+    args = ap.parse_args()
+    rank, local_rank, world = env_int('RANK', 0), env_int('LOCAL_RANK', 0), env_int('WORLD_SIZE', 1)
+    if args.impl == 'reference':
+        return run_reference(args, rank, world)
+    return run_ours(args, rank, local_rank, world)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

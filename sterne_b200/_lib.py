@@ -71,7 +71,8 @@ _lib = None
 
 
 def library_path():
-    return _build.LIB
+    """STERNE_B200_LIB selects an alternative build of the same source (tuning experiments)."""
+    return os.environ.get('STERNE_B200_LIB') or _build.LIB
 
 
 def load(build_if_missing=True):
@@ -81,7 +82,7 @@ def load(build_if_missing=True):
     if _lib is not None:
         return _lib
     path = library_path()
-    if build_if_missing and _build.needs_build():
+    if build_if_missing and path == _build.LIB and _build.needs_build():
         try:
             _build.build_library()
         except Exception as err:

@@ -30,14 +30,15 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force=False, verbose=False, extra=()):
-    if not force and not needs_build():
+def build_library(force=False, verbose=False, extra=(), out=None):
+    """out: alternative output path (tuning experiments); default is the in-tree library."""
+    if out is None and not force and not needs_build():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + list(extra) + ['-o', LIB, SRC]
+    cmd = [nvcc_path()] + NVCC_FLAGS + list(extra) + ['-o', out or LIB, SRC]
     if verbose:
         print(' '.join(cmd))
     subprocess.check_call(cmd)
-    return LIB
+    return out or LIB
 
 
 if __name__ == '__main__':

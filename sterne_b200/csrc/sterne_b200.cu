@@ -38,10 +38,24 @@
 #define STN_MASYR2RADS (4.84813681109536e-09 / (365.25 * 86400.0))
 #define STN_LN2       0.6931471805599453
 
+// build-time tuning knobs (defaults are the measured best; see profiles/)
+#ifndef STN_RBIG
+#define STN_RBIG 2                 /* samples per thread for large batches */
+#endif
+#ifndef STN_RBIG_MINBLOCKS
+#define STN_RBIG_MINBLOCKS 2       /* CTAs per SM the large-batch kernel is compiled for */
+#endif
+#ifndef STN_CHUNK
+#define STN_CHUNK 128
+#endif
+#ifndef STN_RCP_CUBIC
+#define STN_RCP_CUBIC 1            /* 1: cubic refinement of the reciprocal seed, 0: one Newton step */
+#endif
+
 namespace {
 
 constexpr int kThreads = 256;      // threads per CTA of the likelihood kernels
-constexpr int kChunk = 128;        // epochs per shared-memory stage (128 * 96 B = 12 KiB)
+constexpr int kChunk = STN_CHUNK;  // epochs per shared-memory stage (128 * 96 B = 12 KiB)
 constexpr int kStages = 2;
 constexpr int kFirst = 1, kLast = 2;
 
@@ -52,6 +66,8 @@ struct SrcDev {
     int col[STN_NROOTS];
     int efac_on;
     int binary;
+    int grouped;          // EFAC: 4 variances may be multiplied before an exponent extraction
+    int pad;
     double cos_decj;
     double inv_cos_decj;
     double neg_sum_log_err;
@@ -242,66 +258,93 @@ __device__ __forceinline__ double fast_rcp(double v) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(v));
     const double e = fma(-v, y, 1.0);
+#if STN_RCP_CUBIC
     const double p = fma(e, e, e);
     return fma(y, p, y);
+#else
+    return fma(y, e, y);
+#endif
 }
 
-// split a positive normal double into mantissa in [1,2) and unbiased exponent
+// Split a positive normal double into its mantissa in [1,2) and add its BIASED exponent
+// field to esum (one LEA.HI); the bias is removed once per source, 1023 * (number of splits).
 __device__ __forceinline__ double split_exp(double v, int& esum) {
     const int hi = __double2hiint(v);
-    esum += (hi >> 20) - 1023;
+    esum += hi >> 20;
     return __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(v));
 }
 
 struct Acc {
     double chi_ra, chi_dec;   // sum of (res/sigma)^2 per coordinate
-    double prod;              // EFAC: running product of variance mantissas
-    int esum;                 // EFAC: running sum of variance exponents
+    double prod;              // EFAC: running product of variances, renormalised into [1,2)
+    int esum;                 // EFAC: running sum of biased exponents taken out of prod
 };
 
-template <int R, int L, bool EF, bool BIN>
-__device__ __forceinline__ void epoch_loop(const double* __restrict__ rows, int n_epochs, int sub,
-                                           const Coef (&cf)[R], Acc (&acc)[R]) {
-#pragma unroll 2
-    for (int e = sub; e < n_epochs; e += L) {
-        const double2* row = reinterpret_cast<const double2*>(rows + e * STN_FAST_ROW);
-        const double2 tx = row[0];
-        const double2 yz = row[1];
-        const double2 ob = row[2];
-        const double2 aa = row[3];
-        double2 bb = make_double2(0.0, 0.0), bc = make_double2(0.0, 0.0);
-        if (EF) bb = row[4];
-        if (BIN) bc = row[5];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            double ora, odec;
-            fast_offsets<BIN>(cf[r], tx, yz, bc, ora, odec);
-            // model = ref + offset (rad); residual = obs - model   (positions.py:119-120,
-            // simulate.py:368).  This order is kept: the subtraction cancels ~9 digits.
-            const double res_ra = ob.x - (cf[r].ra + ora);
-            const double res_dec = ob.y - (cf[r].dec + odec);
-            if (!EF) {
-                const double z_ra = res_ra * aa.x;
-                const double z_dec = res_dec * aa.y;
-                acc[r].chi_ra = fma(z_ra, z_ra, acc[r].chi_ra);
-                acc[r].chi_dec = fma(z_dec, z_dec, acc[r].chi_dec);
-            } else {
-                const double v_ra = fma(cf[r].g_ra, bb.x, aa.x);     // simulate.py:317
-                const double v_dec = fma(cf[r].g_dec, bb.y, aa.y);
-                const double w_ra = fast_rcp(v_ra);
-                const double w_dec = fast_rcp(v_dec);
-                acc[r].chi_ra = fma(res_ra * res_ra, w_ra, acc[r].chi_ra);
-                acc[r].chi_dec = fma(res_dec * res_dec, w_dec, acc[r].chi_dec);
-                acc[r].prod *= split_exp(v_ra, acc[r].esum);
-                acc[r].prod *= split_exp(v_dec, acc[r].esum);
-            }
+// One epoch of one sample.  EF: the two variances are multiplied into acc.prod
+// (SPLIT_EACH: with an exponent extraction after each, for tables whose variances are
+// so extreme that a product of a few of them could leave the double range).
+template <bool EF, bool BIN, bool SPLIT_EACH>
+__device__ __forceinline__ void epoch_term(const double* __restrict__ rows, int e, const Coef& cf, Acc& acc) {
+    const double2* row = reinterpret_cast<const double2*>(rows + e * STN_FAST_ROW);
+    const double2 tx = row[0];
+    const double2 yz = row[1];
+    const double2 ob = row[2];
+    const double2 aa = row[3];
+    double2 bc = make_double2(0.0, 0.0);
+    if (BIN) bc = row[5];
+    double ora, odec;
+    fast_offsets<BIN>(cf, tx, yz, bc, ora, odec);
+    // model = ref + offset (rad); residual = obs - model   (positions.py:119-120,
+    // simulate.py:368).  This order is kept: the subtraction cancels ~9 digits.
+    const double res_ra = ob.x - (cf.ra + ora);
+    const double res_dec = ob.y - (cf.dec + odec);
+    if (!EF) {
+        const double z_ra = res_ra * aa.x;
+        const double z_dec = res_dec * aa.y;
+        acc.chi_ra = fma(z_ra, z_ra, acc.chi_ra);
+        acc.chi_dec = fma(z_dec, z_dec, acc.chi_dec);
+    } else {
+        const double2 bb = row[4];
+        const double v_ra = fma(cf.g_ra, bb.x, aa.x);     // simulate.py:317
+        const double v_dec = fma(cf.g_dec, bb.y, aa.y);
+        acc.chi_ra = fma(res_ra * res_ra, fast_rcp(v_ra), acc.chi_ra);
+        acc.chi_dec = fma(res_dec * res_dec, fast_rcp(v_dec), acc.chi_dec);
+        if (SPLIT_EACH) {
+            acc.prod = split_exp(acc.prod * v_ra, acc.esum);
+            acc.prod = split_exp(acc.prod * v_dec, acc.esum);
+        } else {
+            acc.prod *= v_ra;
+            acc.prod *= v_dec;
         }
     }
-    if (EF) {
-        // at most 2*kChunk mantissas in [1,2) were multiplied: renormalise
+}
+
+// Returns the number of exponent extractions made per sample (the same for every sample
+// of the thread).  !SPLIT_EACH: one extraction per two epochs (four variances); the host
+// enables it only when four variances cannot overflow / underflow (see stn_create).
+template <int R, int L, bool EF, bool BIN, bool SPLIT_EACH>
+__device__ __forceinline__ int epoch_loop(const double* __restrict__ rows, int n_epochs, int sub,
+                                          const Coef (&cf)[R], Acc (&acc)[R]) {
+    int e = sub;
+#pragma unroll 1
+    for (; e + L < n_epochs; e += 2 * L) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) acc[r].prod = split_exp(acc[r].prod, acc[r].esum);
+        for (int r = 0; r < R; ++r) {
+            epoch_term<EF, BIN, SPLIT_EACH>(rows, e, cf[r], acc[r]);
+            epoch_term<EF, BIN, SPLIT_EACH>(rows, e + L, cf[r], acc[r]);
+            if (EF && !SPLIT_EACH) acc[r].prod = split_exp(acc[r].prod, acc[r].esum);
+        }
     }
+    if (e < n_epochs) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            epoch_term<EF, BIN, SPLIT_EACH>(rows, e, cf[r], acc[r]);
+            if (EF && !SPLIT_EACH) acc[r].prod = split_exp(acc[r].prod, acc[r].esum);
+        }
+    }
+    // epochs handled by this lane: sub, sub+L, ...
+    const int cnt = sub < n_epochs ? (n_epochs - sub + L - 1) / L : 0;
+    return !EF ? 0 : (SPLIT_EACH ? 2 * cnt : (cnt + 1) / 2);
 }
 
 template <int L>
@@ -344,7 +387,7 @@ __device__ double constraint_terms(const ProbDev& P, const double* __restrict__ 
 // K1: fused FAST log-likelihood
 // ---------------------------------------------------------------------------------
 template <int R, int L>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, (R > 1 ? STN_RBIG_MINBLOCKS : 2))
 stn_loglike_fast_kernel(const ProbDev P, const double* __restrict__ theta, const int64_t N,
                         const int64_t ld, const int layout, double* __restrict__ out) {
     __shared__ __align__(128) double stage[kStages][kChunk * STN_FAST_ROW];
@@ -379,6 +422,7 @@ stn_loglike_fast_kernel(const ProbDev P, const double* __restrict__ theta, const
     double logl[R];
     Coef cf[R];
     Acc acc[R];
+    int nsplit = 0;
 #pragma unroll
     for (int r = 0; r < R; ++r) logl[r] = 0.0;
 
@@ -406,10 +450,14 @@ stn_loglike_fast_kernel(const ProbDev P, const double* __restrict__ theta, const
         const double* rows = stage[c & 1];
         const bool ef = S.efac_on != 0;
         const bool bin = S.binary != 0;
-        if (!ef && !bin) epoch_loop<R, L, false, false>(rows, ck.n_epochs, sub, cf, acc);
-        else if (ef && !bin) epoch_loop<R, L, true, false>(rows, ck.n_epochs, sub, cf, acc);
-        else if (!ef && bin) epoch_loop<R, L, false, true>(rows, ck.n_epochs, sub, cf, acc);
-        else epoch_loop<R, L, true, true>(rows, ck.n_epochs, sub, cf, acc);
+        const bool grouped = S.grouped != 0;
+        if (ck.flags & kFirst) nsplit = 0;
+        if (!ef && !bin) epoch_loop<R, L, false, false, false>(rows, ck.n_epochs, sub, cf, acc);
+        else if (!ef && bin) epoch_loop<R, L, false, true, false>(rows, ck.n_epochs, sub, cf, acc);
+        else if (ef && !bin && grouped) nsplit += epoch_loop<R, L, true, false, false>(rows, ck.n_epochs, sub, cf, acc);
+        else if (ef && bin && grouped) nsplit += epoch_loop<R, L, true, true, false>(rows, ck.n_epochs, sub, cf, acc);
+        else if (ef && !bin) nsplit += epoch_loop<R, L, true, false, true>(rows, ck.n_epochs, sub, cf, acc);
+        else nsplit += epoch_loop<R, L, true, true, true>(rows, ck.n_epochs, sub, cf, acc);
 
         if (ck.flags & kLast) {
 #pragma unroll
@@ -419,7 +467,7 @@ stn_loglike_fast_kernel(const ProbDev P, const double* __restrict__ theta, const
                 double logdet;
                 if (ef) {
                     // -sum(log sigma) = -0.5 * log(prod of variances)
-                    const double part = log(acc[r].prod) + (double)acc[r].esum * STN_LN2;
+                    const double part = log(acc[r].prod) + (double)(acc[r].esum - 1023 * nsplit) * STN_LN2;
                     logdet = -0.5 * group_sum<L>(part);
                 } else {
                     logdet = S.neg_sum_log_err;
@@ -589,7 +637,7 @@ stn_model_kernel(const ProbDev P, const int source, const double* __restrict__ t
 __global__ void __launch_bounds__(256) stn_dfma_peak_kernel(double* sink, int iters, double a, double b) {
     double x0 = threadIdx.x * 1e-9, x1 = x0 + 1.0, x2 = x0 + 2.0, x3 = x0 + 3.0;
     double x4 = x0 + 4.0, x5 = x0 + 5.0, x6 = x0 + 6.0, x7 = x0 + 7.0;
-#pragma unroll 4
+#pragma unroll 16
     for (int i = 0; i < iters; ++i) {
         x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
         x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
@@ -690,7 +738,7 @@ int launch_loglike(StnCtx* ctx, const double* theta, int64_t n, int64_t ld, int 
         case 1:
             // R only changes how samples map to threads, never a result bit
             if (n >= (int64_t)4 * ctx->sm_count * kThreads)
-                return launch_fast<2, 1>(ctx, theta, n, ld, layout, out, st);
+                return launch_fast<STN_RBIG, 1>(ctx, theta, n, ld, layout, out, st);
             return launch_fast<1, 1>(ctx, theta, n, ld, layout, out, st);
         case 2: return launch_fast<1, 2>(ctx, theta, n, ld, layout, out, st);
         case 4: return launch_fast<1, 4>(ctx, theta, n, ld, layout, out, st);
@@ -771,6 +819,19 @@ int stn_create(const StnProblem* pb, int device, StnCtx** out_ctx) {
         for (int r = 0; r < STN_NROOTS; ++r) d.col[r] = hs.col[r];
         d.efac_on = hs.efac_on ? 1 : 0;
         d.binary = hs.binary ? 1 : 0;
+        d.grouped = 0;
+        if (d.efac_on) {
+            // variance v = a + g*b with a = err_random^2, b = err_sys^2, g = efac^2 >= 0:
+            // v >= a_min, and v^4 stays far inside the double range for any efac below ~1e45
+            // when the table is within these bounds (radians-scale errors are ~1e-19..1e-9).
+            double a_min = 1e300, a_max = 0.0, b_max = 0.0;
+            for (int64_t e = 0; e < hs.n_epochs; ++e) {
+                const double* row = hs.fast_rows + e * STN_FAST_ROW;
+                for (int k = 6; k < 8; ++k) { if (row[k] < a_min) a_min = row[k]; if (row[k] > a_max) a_max = row[k]; }
+                for (int k = 8; k < 10; ++k) if (row[k] > b_max) b_max = row[k];
+            }
+            d.grouped = (hs.n_epochs > 0 && a_min >= 1e-60 && a_max <= 1e60 && b_max <= 1e30) ? 1 : 0;
+        }
         d.cos_decj = hs.binary ? hs.cos_decj : 1.0;
         d.inv_cos_decj = 1.0 / d.cos_decj;
         d.neg_sum_log_err = hs.neg_sum_log_err;
@@ -907,8 +968,12 @@ int stn_loglike_host(StnCtx* ctx, const double* theta_host, int64_t n, int64_t l
         double* dth = ctx->stage_theta[k & 1];
         double* dout = ctx->stage_out[k & 1];
         int64_t dld;
-        if (layout == STN_LAYOUT_AOS) {
-            // rows are contiguous; keep only the first P columns of each
+        if (layout == STN_LAYOUT_AOS && ld == P) {
+            STN_CUDA(cudaMemcpyAsync(dth, theta_host + lo * ld, (size_t)m * P * sizeof(double),
+                                     cudaMemcpyHostToDevice, st));
+            dld = P;
+        } else if (layout == STN_LAYOUT_AOS) {
+            // padded rows: keep only the first P columns of each
             STN_CUDA(cudaMemcpy2DAsync(dth, (size_t)P * sizeof(double), theta_host + lo * ld,
                                        (size_t)ld * sizeof(double), (size_t)P * sizeof(double), (size_t)m,
                                        cudaMemcpyHostToDevice, st));

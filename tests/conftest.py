@@ -46,3 +46,19 @@ def rel_err(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+
+
+def logl_scale(list_of_dict_VLBI):
+    """Magnitude of the log-determinant part of log-L: sum over sources of |sum(log errs)|.
+
+    log L = -sum(log sigma) - chi^2/2 is a difference of two large positive numbers and
+    crosses zero inside any prior box, where a purely relative error is meaningless.  The
+    1e-10 tolerance is therefore applied relative to max(|log L|, this scale), the size of
+    the terms that were summed (the reference's own rounding error scales the same way)."""
+    return float(sum(abs(np.sum(np.log(np.asarray(v['errs'])))) for v in list_of_dict_VLBI))
+
+
+def logl_err(got, want, scale):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    return np.abs(got - want) / np.maximum(np.abs(want), scale)
