@@ -198,10 +198,11 @@ def run_ours(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    peak_tf, _ = fp64_peak(local_rank, iters=1 << 15, reps=5)
-
     for _ in range(max(args.warmup, 3)):
         step()
+    sync_all()
+    # FP64 roofline denominator, measured with the GPU already warm (37 ms per launch)
+    peak_tf, _ = fp64_peak(local_rank, iters=1 << 17, reps=5)
     sync_all()
     sampler = ClockSampler(local_rank)
     if rank == 0:
