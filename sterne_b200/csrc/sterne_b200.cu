@@ -39,11 +39,14 @@
 #define STN_LN2       0.6931471805599453
 
 // build-time tuning knobs (defaults are the measured best; see profiles/)
+// Samples per thread for large batches.  Measured on B200 at N = 2^22 x 8 x 1024:
+// without EFAC R = 2 (128 registers, 2 CTAs/SM) wins, 30.5 vs 32.4 ms; with EFAC the longer
+// loop body prefers R = 3 (198 registers, 1 CTA/SM, no spills), 52.5 vs 56.3 ms.
 #ifndef STN_RBIG
-#define STN_RBIG 2                 /* samples per thread for large batches */
+#define STN_RBIG 2
 #endif
-#ifndef STN_RBIG_MINBLOCKS
-#define STN_RBIG_MINBLOCKS 2       /* CTAs per SM the large-batch kernel is compiled for */
+#ifndef STN_RBIG_EFAC
+#define STN_RBIG_EFAC 3
 #endif
 #ifndef STN_CHUNK
 #define STN_CHUNK 128
@@ -307,14 +310,20 @@ __device__ __forceinline__ void epoch_term(const double* __restrict__ rows, int 
         const double2 bb = row[4];
         const double v_ra = fma(cf.g_ra, bb.x, aa.x);     // simulate.py:317
         const double v_dec = fma(cf.g_dec, bb.y, aa.y);
-        acc.chi_ra = fma(res_ra * res_ra, fast_rcp(v_ra), acc.chi_ra);
-        acc.chi_dec = fma(res_dec * res_dec, fast_rcp(v_dec), acc.chi_dec);
         if (SPLIT_EACH) {
+            acc.chi_ra = fma(res_ra * res_ra, fast_rcp(v_ra), acc.chi_ra);
+            acc.chi_dec = fma(res_dec * res_dec, fast_rcp(v_dec), acc.chi_dec);
             acc.prod = split_exp(acc.prod * v_ra, acc.esum);
             acc.prod = split_exp(acc.prod * v_dec, acc.esum);
         } else {
-            acc.prod *= v_ra;
-            acc.prod *= v_dec;
+            // one reciprocal for both coordinates: r_a^2/v_a + r_d^2/v_d = (r_a^2 v_d + r_d^2 v_a)/(v_a v_d);
+            // the product v_a v_d is also this epoch's factor of the log-determinant
+            const double p = v_ra * v_dec;
+            const double w = fast_rcp(p);
+            double s = (res_ra * res_ra) * v_dec;
+            s = fma(res_dec * res_dec, v_ra, s);
+            acc.chi_ra = fma(s, w, acc.chi_ra);
+            acc.prod *= p;
         }
     }
 }
@@ -387,7 +396,7 @@ __device__ double constraint_terms(const ProbDev& P, const double* __restrict__ 
 // K1: fused FAST log-likelihood
 // ---------------------------------------------------------------------------------
 template <int R, int L>
-__global__ void __launch_bounds__(kThreads, (R > 1 ? STN_RBIG_MINBLOCKS : 2))
+__global__ void __launch_bounds__(kThreads, (R > 2 ? 1 : 2))
 stn_loglike_fast_kernel(const ProbDev P, const double* __restrict__ theta, const int64_t N,
                         const int64_t ld, const int layout, double* __restrict__ out) {
     __shared__ __align__(128) double stage[kStages][kChunk * STN_FAST_ROW];
@@ -678,6 +687,7 @@ struct StnCtx {
     std::vector<void*> dev_allocs;
     std::vector<int> n_epochs;          // per source
     int max_epochs = 0;
+    bool efac_heavy = false;            // at least half of the epochs belong to EFAC sources
     int64_t launches = 0;
     // *_host staging
     cudaStream_t streams[2] = {nullptr, nullptr};
@@ -738,7 +748,8 @@ int launch_loglike(StnCtx* ctx, const double* theta, int64_t n, int64_t ld, int 
         case 1:
             // R only changes how samples map to threads, never a result bit
             if (n >= (int64_t)4 * ctx->sm_count * kThreads)
-                return launch_fast<STN_RBIG, 1>(ctx, theta, n, ld, layout, out, st);
+                return ctx->efac_heavy ? launch_fast<STN_RBIG_EFAC, 1>(ctx, theta, n, ld, layout, out, st)
+                                       : launch_fast<STN_RBIG, 1>(ctx, theta, n, ld, layout, out, st);
             return launch_fast<1, 1>(ctx, theta, n, ld, layout, out, st);
         case 2: return launch_fast<1, 2>(ctx, theta, n, ld, layout, out, st);
         case 4: return launch_fast<1, 4>(ctx, theta, n, ld, layout, out, st);
@@ -852,6 +863,11 @@ int stn_create(const StnProblem* pb, int device, StnCtx** out_ctx) {
             if (done >= d.n_epochs) c.flags |= kLast;
             chunks.push_back(c);
         } while (done < d.n_epochs);
+    }
+    {
+        int64_t ef = 0, all = 0;
+        for (const SrcDev& d : src) { all += d.n_epochs; if (d.efac_on) ef += d.n_epochs; }
+        ctx->efac_heavy = all > 0 && 2 * ef >= all;
     }
     for (int k = 0; k < pb->n_a1dot; ++k)
         if (pb->a1dot_source[k] < 0 || pb->a1dot_source[k] >= pb->n_sources)

@@ -221,6 +221,8 @@ def positions(refepoch, epochs, dict_timing, parameter_filter_index, dict_parame
     source `parameter_filter_index` are picked from `dict_parameters` exactly as the
     reference does (missing roots = -999).  Device contexts are cached per
     (refepoch, epochs, parfile) so repeated calls only launch the model kernel."""
+    from .readers import plain_timing
+    dict_timing = plain_timing(dict_timing)
     epochs = np.ascontiguousarray(epochs, dtype=np.float64)
     FP = filter_dictionary_of_parameter_with_index(dict_parameters, parameter_filter_index)
     keys = sorted(FP.keys())

@@ -11,6 +11,7 @@ from . import _lib
 from .constants import ROOTS, D2YR, DEG2RAD, C_M_S
 from .ephemeris import earth_vectors
 from .orbit import orbit_terms
+from .readers import plain_timing
 from .shares import get_parameters_from_shares, column_table
 
 R_DEC, R_EFAC, R_EFAD, R_INCL, R_MU_A, R_MU_D, R_OM_ASC, R_PX, R_RA = range(9)
@@ -39,6 +40,7 @@ class CompiledProblem(object):
             raise ValueError('every row of shares must have one entry per pmparin (%d)' % S)
         self.refepoch = refepoch
         self.n_sources = S
+        list_of_dict_timing = [plain_timing(t) for t in list_of_dict_timing]
         self.default_names = list(get_parameters_from_shares(shares))
         self.names = list(self.default_names) if names is None else list(names)
         if sorted(self.names) != sorted(self.default_names):

@@ -161,3 +161,14 @@ def read_inits(initsfile):
                 elif fields[5] == 'Sine_limits':
                     constraints['sin_incl_limits_constraints'][name] = pair
     return limits_by_name, constraints
+
+
+def plain_timing(dict_timing):
+    """Orbital dict with plain floats.  Accepts what the reference's read_parfile returns
+    (astropy Quantities: value taken in the Quantity's own unit, which the reference fixes
+    at reflex_motion.py:76-93 -- pb d, a1 m, t0 d, om deg, omdot deg/yr, a1dot m/s, decj deg)
+    as well as this package's plain-float dicts."""
+    out = {}
+    for k, v in dict_timing.items():
+        out[k] = float(getattr(v, 'value', v))
+    return out

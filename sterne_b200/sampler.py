@@ -1,0 +1,224 @@
+"""Sampler adaptor: hands whole walker / live-point batches to the GPU.
+
+The reference runs bilby's emcee wrapper, which calls `log_likelihood()` once per walker
+per step from Python (simulate.py:191-192).  Here a sampler sees ONE call per step:
+
+* `BoxPrior`            batched log-prior for the `.inits` kinds Uniform / Gaussian / Sine plus
+                        the sin(incl) limits constraint (priors.py:344-377), numpy or torch;
+* `log_prob_fn`         a vectorised log-posterior `(nwalkers, ndim) -> (nwalkers,)` for
+                        `emcee.EnsembleSampler(..., vectorize=True)`;
+* `BatchPool`           a `pool.map` shim for samplers that evaluate lists of points through a
+                        pool (dynesty `queue_size`, bilby `npool`): the whole list is one batch;
+* `EnsembleSampler`     a small built-in affine-invariant stretch-move sampler (Goodman & Weare
+                        2010; the algorithm emcee implements) that keeps walkers on the device,
+                        so BASELINE config 2 (4096 walkers) runs without emcee, which is not
+                        installed in this image.
+"""
+import math
+import numpy as np
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith('torch')
+
+
+class BoxPrior(object):
+    """Independent priors from an `.inits` limits dict {name: [a, b, kind]} (priors.py:356-366):
+    Uniform(a, b), Gaussian(mu=a, sigma=b), Sine(a, b) [density ~ sin x on (a, b)], plus the
+    optional {name: [lo, hi]} limits on sin(incl) (bilby Constraint, priors.py:351-354)."""
+
+    def __init__(self, limits, constraints=None, keys=None):
+        self.keys = list(limits.keys()) if keys is None else list(keys)
+        kinds, a, b = [], [], []
+        for k in self.keys:
+            lo, hi, kind = limits[k][0], limits[k][1], limits[k][2]
+            if kind not in ('Uniform', 'Gaussian', 'Sine'):
+                raise ValueError('unknown prior kind %r for %s' % (kind, k))
+            kinds.append(kind)
+            a.append(float(lo))
+            b.append(float(hi))
+        self.kinds = kinds
+        self.a = np.array(a)
+        self.b = np.array(b)
+        silc = {} if constraints is None else constraints.get('sin_incl_limits_constraints', {})
+        self.sin_limits = [(self.keys.index(k), float(v[0]), float(v[1])) for k, v in silc.items()]
+        self._const = 0.0
+        for kind, lo, hi in zip(kinds, a, b):
+            if kind == 'Uniform':
+                self._const += -math.log(hi - lo)
+            elif kind == 'Gaussian':
+                self._const += -math.log(hi) - 0.5 * math.log(2.0 * math.pi)
+            else:
+                self._const += -math.log(math.cos(lo) - math.cos(hi))
+        self._dev = {}
+
+    @property
+    def ndim(self):
+        return len(self.keys)
+
+    def sample(self, n, seed=0):
+        rng = np.random.default_rng(seed)
+        out = np.empty((n, self.ndim))
+        for j, kind in enumerate(self.kinds):
+            if kind == 'Uniform':
+                out[:, j] = rng.uniform(self.a[j], self.b[j], n)
+            elif kind == 'Gaussian':
+                out[:, j] = rng.normal(self.a[j], self.b[j], n)
+            else:
+                u = rng.random(n)
+                out[:, j] = np.arccos(np.cos(self.a[j]) - u * (np.cos(self.a[j]) - np.cos(self.b[j])))
+        return out
+
+    def log_prob(self, theta):
+        """(N, ndim) -> (N,) log prior density (−inf outside the support)."""
+        if _is_torch(theta):
+            return self._log_prob_torch(theta)
+        theta = np.asarray(theta, dtype=np.float64)
+        lp = np.full(theta.shape[0], self._const)
+        for j, kind in enumerate(self.kinds):
+            x = theta[:, j]
+            if kind == 'Gaussian':
+                lp += -0.5 * ((x - self.a[j]) / self.b[j]) ** 2
+            else:
+                inside = (x >= self.a[j]) & (x <= self.b[j])
+                if kind == 'Sine':
+                    with np.errstate(divide='ignore', invalid='ignore'):
+                        lp += np.where(inside, np.log(np.where(inside, np.sin(x), 1.0)), 0.0)
+                lp = np.where(inside, lp, -np.inf)
+        for j, lo, hi in self.sin_limits:
+            s = np.sin(theta[:, j])
+            lp = np.where((s >= lo) & (s <= hi), lp, -np.inf)
+        return lp
+
+    def _log_prob_torch(self, theta):
+        import torch
+        key = str(theta.device)
+        if key not in self._dev:
+            self._dev[key] = (torch.as_tensor(self.a, device=theta.device), torch.as_tensor(self.b, device=theta.device))
+        a, b = self._dev[key]
+        ninf = torch.tensor(-math.inf, dtype=theta.dtype, device=theta.device)
+        lp = torch.full((theta.shape[0],), self._const, dtype=theta.dtype, device=theta.device)
+        for j, kind in enumerate(self.kinds):
+            x = theta[:, j]
+            if kind == 'Gaussian':
+                lp = lp - 0.5 * ((x - a[j]) / b[j]) ** 2
+            else:
+                inside = (x >= a[j]) & (x <= b[j])
+                if kind == 'Sine':
+                    lp = lp + torch.where(inside, torch.log(torch.where(inside, torch.sin(x), torch.ones_like(x))),
+                                          torch.zeros_like(x))
+                lp = torch.where(inside, lp, ninf)
+        for j, lo, hi in self.sin_limits:
+            s = torch.sin(theta[:, j])
+            lp = torch.where((s >= lo) & (s <= hi), lp, ninf)
+        return lp
+
+
+def log_prob_fn(likelihood, prior):
+    """Vectorised log-posterior for emcee (vectorize=True) and the built-in sampler.  Points
+    outside the prior support are not sent through the likelihood's arithmetic result."""
+    keys = prior.keys
+
+    def fn(theta):
+        lp = prior.log_prob(theta)
+        ll = likelihood.log_likelihood_batch(theta, keys=keys)
+        if _is_torch(theta):
+            import torch
+            return torch.where(torch.isfinite(lp), lp + ll, lp)
+        return np.where(np.isfinite(lp), lp + ll, lp)
+
+    return fn
+
+
+class BatchPool(object):
+    """`pool.map(fn, list_of_points)` -> one batched GPU call.  Use with samplers that
+    evaluate several points per iteration through a pool (dynesty: pool=BatchPool(like, keys),
+    queue_size=K).  `fn` is ignored when it is the sampler's own likelihood wrapper: the batch
+    goes to `likelihood.log_likelihood_batch`."""
+
+    def __init__(self, likelihood, keys, size=1024):
+        self.like = likelihood
+        self.keys = list(keys)
+        self.size = int(size)
+
+    def map(self, fn, points):
+        pts = list(points)
+        if len(pts) == 0:
+            return []
+        theta = np.asarray(pts, dtype=np.float64).reshape(len(pts), -1)
+        return list(self.like.log_likelihood_batch(theta, keys=self.keys))
+
+    def close(self):
+        pass
+
+    def join(self):
+        pass
+
+
+class EnsembleSampler(object):
+    """Affine-invariant ensemble sampler with the stretch move, red/blue split so that each
+    half-step is ONE batched log-probability call.  State lives in torch tensors on
+    `device` (CUDA for the product; CPU tensors work too and are what the CPU tests use).
+
+        s = EnsembleSampler(nwalkers, ndim, log_prob, device='cuda:0')
+        s.run(p0, nsteps);  chain = s.chain  # (nsteps, nwalkers, ndim)
+    """
+
+    def __init__(self, nwalkers, ndim, log_prob, a=2.0, device='cpu', seed=0):
+        import torch
+        if nwalkers % 2 or nwalkers < 2 * ndim:
+            raise ValueError('nwalkers must be even and at least 2*ndim')
+        self.torch = torch
+        self.nwalkers, self.ndim, self.a = nwalkers, ndim, float(a)
+        self.log_prob = log_prob
+        self.device = torch.device(device)
+        self.gen = torch.Generator(device=self.device)
+        self.gen.manual_seed(seed)
+        self.chain = None
+        self.lnprob = None
+        self.naccepted = torch.zeros((), dtype=torch.int64, device=self.device)
+        self.nproposed = 0
+        self.ncalls = 0
+
+    def _call(self, x):
+        self.ncalls += 1
+        out = self.log_prob(x)
+        if not _is_torch(out):
+            out = self.torch.as_tensor(np.asarray(out), device=self.device)
+        return out.to(self.torch.float64)
+
+    def run(self, p0, nsteps, store=True):
+        torch = self.torch
+        x = torch.as_tensor(np.asarray(p0) if not _is_torch(p0) else p0).to(self.device, torch.float64).clone()
+        lp = self._call(x)
+        if not bool(torch.isfinite(lp).all()):
+            raise ValueError('initial walkers must have finite log-probability')
+        half = self.nwalkers // 2
+        if store:
+            self.chain = torch.empty((nsteps, self.nwalkers, self.ndim), dtype=torch.float64, device=self.device)
+            self.lnprob = torch.empty((nsteps, self.nwalkers), dtype=torch.float64, device=self.device)
+        sets = (slice(0, half), slice(half, self.nwalkers))
+        for t in range(nsteps):
+            for k in (0, 1):
+                S, C = sets[k], sets[1 - k]
+                u = torch.rand(half, generator=self.gen, device=self.device, dtype=torch.float64)
+                z = ((self.a - 1.0) * u + 1.0) ** 2 / self.a                      # g(z) ~ 1/sqrt(z) on [1/a, a]
+                j = torch.randint(0, half, (half,), generator=self.gen, device=self.device)
+                y = x[C][j] + z[:, None] * (x[S] - x[C][j])
+                lpy = self._call(y)
+                lnq = (self.ndim - 1.0) * torch.log(z) + lpy - lp[S]
+                acc = torch.log(torch.rand(half, generator=self.gen, device=self.device, dtype=torch.float64)) < lnq
+                acc = acc & torch.isfinite(lpy)
+                x[S] = torch.where(acc[:, None], y, x[S])
+                lp[S] = torch.where(acc, lpy, lp[S])
+                self.naccepted += acc.sum()
+                self.nproposed += half
+            if store:
+                self.chain[t] = x
+                self.lnprob[t] = lp
+        self.last = (x, lp)
+        return x, lp
+
+    @property
+    def acceptance_fraction(self):
+        return float(self.naccepted) / max(self.nproposed, 1)
