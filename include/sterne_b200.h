@@ -12,8 +12,9 @@
  *
  * Ownership: the caller owns every buffer it passes in.  The library owns only the
  * context (device copies of the epoch tables made by stn_create, plus staging
- * buffers used by the *_host entry points).  A context is immutable after creation
- * and may be used from one thread at a time.
+ * buffers used by the *_host entry points).  A context's problem is immutable after
+ * creation (only the optional prior can be replaced, stn_set_prior); use a context from
+ * one thread at a time.
  */
 #ifndef STERNE_B200_H
 #define STERNE_B200_H
@@ -106,6 +107,22 @@ typedef struct StnProblem {
     const double* sini_sigma;
 } StnProblem;
 
+/* Independent per-parameter priors of the reference's .inits kinds (priors.py:356-366), so a
+ * sampler's log-posterior is ONE launch.  Uniform(a,b); Gaussian(mu=a, sigma=b); Sine(a,b)
+ * [density ~ sin x on (a,b)]; plus the limits on sin(incl) (bilby Constraint, priors.py:351-354). */
+enum StnPriorKind { STN_PRIOR_UNIFORM = 1, STN_PRIOR_GAUSSIAN = 2, STN_PRIOR_SINE = 3 };
+
+typedef struct StnPrior {
+    int32_t n_params;            /* must equal the problem's P; one entry per theta column */
+    const int32_t* kind;         /* StnPriorKind */
+    const double* a;
+    const double* b;
+    int32_t n_sin_limits;        /* lo <= sin(theta[col]) <= hi */
+    const int32_t* sin_col;
+    const double* sin_lo;
+    const double* sin_hi;
+} StnPrior;
+
 typedef struct StnCtx StnCtx;
 
 int stn_version(void);
@@ -126,7 +143,16 @@ int stn_destroy(StnCtx* ctx);
 int stn_loglike(StnCtx* ctx, const double* theta_dev, int64_t n, int64_t ld,
                 int layout, int mode, int lanes, double* out_dev, void* stream);
 
-/* Same, HOST buffers: H2D copy, kernel(s), D2H copy, synchronised on return.
+/* Installs (copies) the prior used by stn_logpost.  Replaces: priors.create_priors_given_limits_dict
+ * (priors.py:344-366) evaluated per walker by bilby. */
+int stn_set_prior(StnCtx* ctx, const StnPrior* prior);
+
+/* log prior + log likelihood for n vectors; -inf outside the prior's support.  Same
+ * arguments as stn_loglike.  Requires stn_set_prior. */
+int stn_logpost(StnCtx* ctx, const double* theta_dev, int64_t n, int64_t ld,
+                int layout, int mode, int lanes, double* out_dev, void* stream);
+
+/* Batched log-likelihood, HOST buffers: H2D copy, kernel(s), D2H copy, synchronised on return.
  * Large batches are cut into chunks whose copies overlap the kernels.  Pinned
  * buffers (stn_host_alloc) are copied at full PCIe rate. */
 int stn_loglike_host(StnCtx* ctx, const double* theta_host, int64_t n, int64_t ld,

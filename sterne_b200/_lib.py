@@ -28,6 +28,20 @@ class StnSource(ctypes.Structure):
                 ('a1_lts', ctypes.c_double)]
 
 
+class StnPrior(ctypes.Structure):
+    _fields_ = [('n_params', ctypes.c_int32),
+                ('kind', c_int32_p),
+                ('a', c_double_p),
+                ('b', c_double_p),
+                ('n_sin_limits', ctypes.c_int32),
+                ('sin_col', c_int32_p),
+                ('sin_lo', c_double_p),
+                ('sin_hi', c_double_p)]
+
+
+PRIOR_KINDS = {'Uniform': 1, 'Gaussian': 2, 'Sine': 3}
+
+
 class StnProblem(ctypes.Structure):
     _fields_ = [('n_sources', ctypes.c_int32),
                 ('n_params', ctypes.c_int32),
@@ -52,6 +66,8 @@ SYMBOLS = [
     ('stn_create', _int, [ctypes.POINTER(StnProblem), _int, ctypes.POINTER(_vp)]),
     ('stn_destroy', _int, [_vp]),
     ('stn_loglike', _int, [_vp, _vp, _i64, _i64, _int, _int, _int, _vp, _vp]),
+    ('stn_set_prior', _int, [_vp, ctypes.POINTER(StnPrior)]),
+    ('stn_logpost', _int, [_vp, _vp, _i64, _i64, _int, _int, _int, _vp, _vp]),
     ('stn_loglike_host', _int, [_vp, _vp, _i64, _i64, _int, _int, _int, _vp]),
     ('stn_model', _int, [_vp, _int, _vp, _i64, _i64, _int, _int, _vp, _vp, _vp]),
     ('stn_auto_lanes', _int, [_vp, _i64]),

@@ -22,6 +22,7 @@
 #include "sterne_b200.h"
 
 #include <cuda_runtime.h>
+#include <math_constants.h>
 #include <cstdio>
 #include <cstdarg>
 #include <cstring>
@@ -87,6 +88,14 @@ struct ChunkDev {
 
 struct ProbDev {
     int n_sources, n_params, n_chunks, n_a1dot, n_sini;
+    int n_prior, n_sinlim, pad0;      // n_prior = 0: likelihood only
+    double prior_const;               // sum of the priors' normalisation terms
+    const int* prior_kind;
+    const double* prior_a;
+    const double* prior_b;
+    const int* sinlim_col;
+    const double* sinlim_lo;
+    const double* sinlim_hi;
     const SrcDev* src;
     const ChunkDev* chunks;
     const int* a1_src;
@@ -392,6 +401,30 @@ __device__ double constraint_terms(const ProbDev& P, const double* __restrict__ 
     return add;
 }
 
+// log prior of one parameter vector (priors.py:356-366; -inf outside the support)
+__device__ double prior_terms(const ProbDev& P, const double* __restrict__ theta, int64_t n, int64_t ld,
+                              int layout) {
+    double lp = P.prior_const;
+    bool inside = true;
+    for (int k = 0; k < P.n_prior; ++k) {
+        const double x = load_param(theta, n, k, ld, layout);
+        const double a = P.prior_a[k], b = P.prior_b[k];
+        const int kind = P.prior_kind[k];
+        if (kind == STN_PRIOR_GAUSSIAN) {
+            const double z = (x - a) / b;
+            lp += -0.5 * (z * z);
+        } else {
+            inside = inside && (x >= a) && (x <= b);
+            if (kind == STN_PRIOR_SINE) lp += log(sin(x));
+        }
+    }
+    for (int k = 0; k < P.n_sinlim; ++k) {
+        const double sx = sin(load_param(theta, n, P.sinlim_col[k], ld, layout));
+        inside = inside && (sx >= P.sinlim_lo[k]) && (sx <= P.sinlim_hi[k]);
+    }
+    return inside ? lp : -CUDART_INF;
+}
+
 // ---------------------------------------------------------------------------------
 // K1: fused FAST log-likelihood
 // ---------------------------------------------------------------------------------
@@ -491,6 +524,10 @@ stn_loglike_fast_kernel(const ProbDev P, const double* __restrict__ theta, const
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         if (P.n_a1dot > 0 || P.n_sini > 0) logl[r] += constraint_terms(P, theta, nidx[r], ld, layout);
+        if (P.n_prior > 0) {
+            const double lp = prior_terms(P, theta, nidx[r], ld, layout);
+            logl[r] = (lp == -CUDART_INF) ? lp : logl[r] + lp;
+        }
         if (valid[r] && sub == 0) out[nidx[r]] = logl[r];
     }
 }
@@ -597,6 +634,10 @@ stn_loglike_strict_kernel(const ProbDev P, const double* __restrict__ theta, con
         logl = __dadd_rn(logl, S.efac_on ? -slog : S.neg_sum_log_err);
     }
     if (P.n_a1dot > 0 || P.n_sini > 0) logl += constraint_terms(P, theta, n, ld, layout);
+    if (P.n_prior > 0) {
+        const double lp = prior_terms(P, theta, n, ld, layout);
+        logl = (lp == -CUDART_INF) ? lp : logl + lp;
+    }
     out[n] = logl;
 }
 
@@ -687,6 +728,9 @@ struct StnCtx {
     std::vector<void*> dev_allocs;
     std::vector<int> n_epochs;          // per source
     int max_epochs = 0;
+    ProbDev prior_prob{};               // copy of prob with the prior switched on (stn_set_prior)
+    bool has_prior = false;
+    std::vector<void*> prior_allocs;
     bool efac_heavy = false;            // at least half of the epochs belong to EFAC sources
     int64_t launches = 0;
     // *_host staging
@@ -722,23 +766,24 @@ int pick_lanes(const StnCtx* ctx, int64_t n) {
 }
 
 template <int R, int L>
-int launch_fast(StnCtx* ctx, const double* theta, int64_t n, int64_t ld, int layout, double* out,
-                cudaStream_t st) {
+int launch_fast(StnCtx* ctx, const ProbDev& prob, const double* theta, int64_t n, int64_t ld, int layout,
+                double* out, cudaStream_t st) {
     constexpr int per_cta = (kThreads / L) * R;
     const int64_t grid = (n + per_cta - 1) / per_cta;
     if (grid > 0x7fffffffLL) return fail(STN_ERR_INVALID, "batch too large for one launch");
-    stn_loglike_fast_kernel<R, L><<<(unsigned)grid, kThreads, 0, st>>>(ctx->prob, theta, n, ld, layout, out);
+    stn_loglike_fast_kernel<R, L><<<(unsigned)grid, kThreads, 0, st>>>(prob, theta, n, ld, layout, out);
     STN_CUDA(cudaGetLastError());
     ctx->launches++;
     return STN_OK;
 }
 
 int launch_loglike(StnCtx* ctx, const double* theta, int64_t n, int64_t ld, int layout, int mode,
-                   int lanes, double* out, cudaStream_t st) {
+                   int lanes, double* out, cudaStream_t st, bool with_prior = false) {
     if (n == 0) return STN_OK;
+    const ProbDev& prob = with_prior ? ctx->prior_prob : ctx->prob;
     if (mode == STN_MODE_STRICT) {
         const int64_t grid = (n + kThreads - 1) / kThreads;
-        stn_loglike_strict_kernel<<<(unsigned)grid, kThreads, 0, st>>>(ctx->prob, theta, n, ld, layout, out);
+        stn_loglike_strict_kernel<<<(unsigned)grid, kThreads, 0, st>>>(prob, theta, n, ld, layout, out);
         STN_CUDA(cudaGetLastError());
         ctx->launches++;
         return STN_OK;
@@ -748,14 +793,14 @@ int launch_loglike(StnCtx* ctx, const double* theta, int64_t n, int64_t ld, int 
         case 1:
             // R only changes how samples map to threads, never a result bit
             if (n >= (int64_t)4 * ctx->sm_count * kThreads)
-                return ctx->efac_heavy ? launch_fast<STN_RBIG_EFAC, 1>(ctx, theta, n, ld, layout, out, st)
-                                       : launch_fast<STN_RBIG, 1>(ctx, theta, n, ld, layout, out, st);
-            return launch_fast<1, 1>(ctx, theta, n, ld, layout, out, st);
-        case 2: return launch_fast<1, 2>(ctx, theta, n, ld, layout, out, st);
-        case 4: return launch_fast<1, 4>(ctx, theta, n, ld, layout, out, st);
-        case 8: return launch_fast<1, 8>(ctx, theta, n, ld, layout, out, st);
-        case 16: return launch_fast<1, 16>(ctx, theta, n, ld, layout, out, st);
-        case 32: return launch_fast<1, 32>(ctx, theta, n, ld, layout, out, st);
+                return ctx->efac_heavy ? launch_fast<STN_RBIG_EFAC, 1>(ctx, prob, theta, n, ld, layout, out, st)
+                                       : launch_fast<STN_RBIG, 1>(ctx, prob, theta, n, ld, layout, out, st);
+            return launch_fast<1, 1>(ctx, prob, theta, n, ld, layout, out, st);
+        case 2: return launch_fast<1, 2>(ctx, prob, theta, n, ld, layout, out, st);
+        case 4: return launch_fast<1, 4>(ctx, prob, theta, n, ld, layout, out, st);
+        case 8: return launch_fast<1, 8>(ctx, prob, theta, n, ld, layout, out, st);
+        case 16: return launch_fast<1, 16>(ctx, prob, theta, n, ld, layout, out, st);
+        case 32: return launch_fast<1, 32>(ctx, prob, theta, n, ld, layout, out, st);
         default: return fail(STN_ERR_INVALID, "lanes must be 0 or a power of two <= 32 (got %d)", lanes);
     }
 }
@@ -899,6 +944,7 @@ int stn_destroy(StnCtx* ctx) {
     if (!ctx) return STN_OK;
     cudaSetDevice(ctx->device);
     for (void* p : ctx->dev_allocs) cudaFree(p);
+    for (void* p : ctx->prior_allocs) cudaFree(p);
     for (int i = 0; i < 2; ++i) {
         if (ctx->stage_theta[i]) cudaFree(ctx->stage_theta[i]);
         if (ctx->stage_out[i]) cudaFree(ctx->stage_out[i]);
@@ -922,6 +968,71 @@ int stn_loglike(StnCtx* ctx, const double* theta_dev, int64_t n, int64_t ld, int
     if (rc) return rc;
     STN_CUDA(cudaSetDevice(ctx->device));
     return launch_loglike(ctx, theta_dev, n, ld, layout, mode, lanes, out_dev, static_cast<cudaStream_t>(stream));
+}
+
+int stn_set_prior(StnCtx* ctx, const StnPrior* pr) {
+    if (!ctx || !pr) return fail(STN_ERR_INVALID, "null argument");
+    if (pr->n_params != ctx->prob.n_params)
+        return fail(STN_ERR_INVALID, "prior has %d entries, the problem has %d parameters", pr->n_params,
+                    ctx->prob.n_params);
+    if (!pr->kind || !pr->a || !pr->b) return fail(STN_ERR_INVALID, "null prior arrays");
+    double c = 0.0;
+    for (int k = 0; k < pr->n_params; ++k) {
+        const double a = pr->a[k], b = pr->b[k];
+        switch (pr->kind[k]) {
+            case STN_PRIOR_UNIFORM:
+                if (!(b > a)) return fail(STN_ERR_INVALID, "prior %d: Uniform needs a < b", k);
+                c += -std::log(b - a);
+                break;
+            case STN_PRIOR_GAUSSIAN:
+                if (!(b > 0)) return fail(STN_ERR_INVALID, "prior %d: Gaussian needs sigma > 0", k);
+                c += -std::log(b) - 0.5 * std::log(2.0 * 3.14159265358979323846);
+                break;
+            case STN_PRIOR_SINE:
+                if (!(b > a) || a < 0.0 || b > 3.14159265358979323846)
+                    return fail(STN_ERR_INVALID, "prior %d: Sine needs 0 <= a < b <= pi", k);
+                c += -std::log(std::cos(a) - std::cos(b));
+                break;
+            default: return fail(STN_ERR_INVALID, "prior %d: unknown kind %d", k, pr->kind[k]);
+        }
+    }
+    for (int k = 0; k < pr->n_sin_limits; ++k)
+        if (pr->sin_col[k] < 0 || pr->sin_col[k] >= pr->n_params)
+            return fail(STN_ERR_INVALID, "sin limit %d: bad column", k);
+    STN_CUDA(cudaSetDevice(ctx->device));
+    STN_CUDA(cudaDeviceSynchronize());                 // no launch may still read the old prior
+    for (void* p : ctx->prior_allocs) cudaFree(p);
+    ctx->prior_allocs.clear();
+    ctx->has_prior = false;
+    ProbDev P = ctx->prob;
+    // upload() records into dev_allocs; move those entries to prior_allocs so they can be replaced
+    const size_t mark = ctx->dev_allocs.size();
+    int rc = STN_OK;
+    if (!rc) rc = upload(ctx, pr->kind, (size_t)pr->n_params, &P.prior_kind);
+    if (!rc) rc = upload(ctx, pr->a, (size_t)pr->n_params, &P.prior_a);
+    if (!rc) rc = upload(ctx, pr->b, (size_t)pr->n_params, &P.prior_b);
+    if (!rc) rc = upload(ctx, pr->sin_col, (size_t)pr->n_sin_limits, &P.sinlim_col);
+    if (!rc) rc = upload(ctx, pr->sin_lo, (size_t)pr->n_sin_limits, &P.sinlim_lo);
+    if (!rc) rc = upload(ctx, pr->sin_hi, (size_t)pr->n_sin_limits, &P.sinlim_hi);
+    ctx->prior_allocs.assign(ctx->dev_allocs.begin() + mark, ctx->dev_allocs.end());
+    ctx->dev_allocs.resize(mark);
+    if (rc) return rc;
+    P.n_prior = pr->n_params;
+    P.n_sinlim = pr->n_sin_limits;
+    P.prior_const = c;
+    ctx->prior_prob = P;
+    ctx->has_prior = true;
+    return STN_OK;
+}
+
+int stn_logpost(StnCtx* ctx, const double* theta_dev, int64_t n, int64_t ld, int layout, int mode,
+                int lanes, double* out_dev, void* stream) {
+    int rc = check_call(ctx, theta_dev, n, ld, layout, mode, out_dev);
+    if (rc) return rc;
+    if (!ctx->has_prior) return fail(STN_ERR_INVALID, "stn_logpost needs stn_set_prior first");
+    STN_CUDA(cudaSetDevice(ctx->device));
+    return launch_loglike(ctx, theta_dev, n, ld, layout, mode, lanes, out_dev, static_cast<cudaStream_t>(stream),
+                          true);
 }
 
 int stn_loglike_timed(StnCtx* ctx, const double* theta_dev, int64_t n, int64_t ld, int layout,

@@ -165,6 +165,30 @@ class Gaussianlikelihood(_LikelihoodBase):
         ctx.loglike_host_ptr(theta.ctypes.data, n, ld, lay, mode, lanes, out.ctypes.data)
         return out
 
+    def log_posterior_batch(self, theta, prior, out=None, mode=None, lanes=None):
+        """log prior + log L of N vectors in ONE launch (stn_logpost); -inf outside the prior's
+        support.  theta: (N, P) float64 CUDA tensor whose columns follow prior.keys
+        (sampler.BoxPrior).  Returns a CUDA tensor."""
+        import torch
+        ctx = self._context(prior.keys)
+        if ctx.prior is not prior:
+            ctx.set_prior(prior)
+        if not _is_torch_tensor(theta) or not theta.is_cuda:
+            raise TypeError('log_posterior_batch takes a CUDA tensor (samplers on the device); use '
+                            'sampler.log_prob_fn for host arrays')
+        if theta.dtype != torch.float64 or theta.dim() != 2:
+            raise TypeError('theta must be a 2-D float64 tensor')
+        if theta.stride(1) != 1:
+            theta = theta.contiguous()
+        mode = self.mode if mode is None else _lib.MODES[mode]
+        lanes = self.lanes if lanes is None else int(lanes)
+        n, ld = self._shape(theta.shape, theta.stride(0), _lib.LAYOUT_AOS, ctx.problem.n_params)
+        if out is None:
+            out = torch.empty(n, dtype=torch.float64, device=theta.device)
+        stream = torch.cuda.current_stream(theta.device).cuda_stream
+        ctx.logpost_ptr(theta.data_ptr(), n, ld, _lib.LAYOUT_AOS, mode, lanes, out.data_ptr(), stream)
+        return out
+
     @staticmethod
     def _shape(shape, stride0, lay, P):
         if lay == _lib.LAYOUT_AOS:

@@ -188,6 +188,7 @@ class DeviceContext(object):
         _lib.check(self.lib.stn_create(ctypes.byref(pb), self.device, ctypes.byref(handle)))
         del keep
         self.handle = handle
+        self.prior = None
 
     def close(self):
         if getattr(self, 'handle', None):
@@ -203,6 +204,33 @@ class DeviceContext(object):
     # ---- raw entry points (pointers are integers: tensor.data_ptr() / ndarray.ctypes.data)
     def loglike_ptr(self, theta_ptr, n, ld, layout, mode, lanes, out_ptr, stream=0):
         _lib.check(self.lib.stn_loglike(self.handle, theta_ptr, n, ld, layout, mode, lanes, out_ptr, stream))
+
+    def set_prior(self, prior):
+        """prior: sampler.BoxPrior whose keys are this context's column order."""
+        import numpy as np
+        if list(prior.keys) != list(self.problem.names):
+            raise ValueError('prior keys %r differ from the context column order %r'
+                             % (prior.keys, self.problem.names))
+        kind = np.array([_lib.PRIOR_KINDS[k] for k in prior.kinds], dtype=np.int32)
+        a = np.ascontiguousarray(prior.a, dtype=np.float64)
+        b = np.ascontiguousarray(prior.b, dtype=np.float64)
+        col = np.array([c for c, _, _ in prior.sin_limits], dtype=np.int32)
+        lo = np.array([l for _, l, _ in prior.sin_limits], dtype=np.float64)
+        hi = np.array([h for _, _, h in prior.sin_limits], dtype=np.float64)
+        pr = _lib.StnPrior()
+        pr.n_params = len(kind)
+        pr.kind = kind.ctypes.data_as(_lib.c_int32_p)
+        pr.a = a.ctypes.data_as(_lib.c_double_p)
+        pr.b = b.ctypes.data_as(_lib.c_double_p)
+        pr.n_sin_limits = len(col)
+        pr.sin_col = col.ctypes.data_as(_lib.c_int32_p)
+        pr.sin_lo = lo.ctypes.data_as(_lib.c_double_p)
+        pr.sin_hi = hi.ctypes.data_as(_lib.c_double_p)
+        _lib.check(self.lib.stn_set_prior(self.handle, ctypes.byref(pr)))
+        self.prior = prior
+
+    def logpost_ptr(self, theta_ptr, n, ld, layout, mode, lanes, out_ptr, stream=0):
+        _lib.check(self.lib.stn_logpost(self.handle, theta_ptr, n, ld, layout, mode, lanes, out_ptr, stream))
 
     def loglike_host_ptr(self, theta_ptr, n, ld, layout, mode, lanes, out_ptr):
         _lib.check(self.lib.stn_loglike_host(self.handle, theta_ptr, n, ld, layout, mode, lanes, out_ptr))

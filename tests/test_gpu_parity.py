@@ -258,3 +258,71 @@ def test_sharded_slices_are_bit_identical():
             parts.append(like.log_likelihood_batch(theta[lo:hi], lanes=lanes))
         assert torch.equal(torch.cat(parts), full), world
     like.close()
+
+
+def _multi_case(seed, epoch_counts, efac=True, binaries=(), a1dot=False):
+    """Hand-built problem: shared px / mu_a / mu_d (/ efac), distinct ra / dec, chosen sources binary."""
+    rng = np.random.default_rng(seed)
+    S = len(epoch_counts)
+    T = synthetic.TRUTH
+    b = dict(synthetic.PARFILE_CFG3)
+    b.update(pb=175.46, ecc=0.3, a1=55.33, t0=56100.25, om=50.7, omdot=0.0123)
+    timing = synthetic.timing_dict(**b)
+    refepoch = 57365.0
+    V, X, TM, pos = [], [], [], []
+    for s, E in enumerate(epoch_counts):
+        ra, dec = T['ra'] + 3e-6 * s, T['dec'] - 2e-6 * s
+        pos.append((ra, dec))
+        tm = timing if s in binaries else {}
+        v, x = synthetic.make_source(rng, refepoch, 57000 + rng.uniform(0, 1500, E), ra, dec, T['mu_a'], T['mu_d'],
+                                     T['px'], timing=tm or None, incl=T['incl'], om_asc=T['om_asc'],
+                                     random_fraction=0.6 if efac else None)
+        V.append(v); X.append(x); TM.append(tm)
+    brow = [0 if s in binaries else -1 for s in range(S)]
+    shares = [list(range(S)), [0] * S if efac else [-1] * S, [-1] * S, brow, [0] * S, [0] * S, list(brow), [0] * S,
+              list(range(S))]
+    names = list(synthetic.get_parameters_from_shares(shares))
+    truth = {}
+    for k in names:
+        srcs, root = synthetic.parameter_name_to_pmparin_indice(k)
+        truth[k] = pos[srcs[0]][0] if root == 'ra' else pos[srcs[0]][1] if root == 'dec' else T[root]
+    a1 = [[1.1e-14, 4e-15] if s in binaries else [] for s in range(S)] if a1dot else False
+    return synthetic.SyntheticCase('multi', refepoch, TM, V, shares, X, truth, synthetic._box_for(names, truth),
+                                   a1dot_constraints=a1)
+
+
+@pytest.mark.parametrize('epoch_counts,binaries,a1dot', [
+    ((7, 0, 3), (), False),                    # a source with NO epochs (empty pmpar.in)
+    ((1, 1), (0,), False),                     # single-epoch sources
+    ((5000,), (0,), False),                    # long series, not a multiple of the 128-epoch stage
+    ((129, 127, 128, 1), (1, 3), True),        # stage boundaries; two binaries sharing incl/om_asc + a1dot terms
+    (tuple([3] * 12), (11,), False),           # 12 sources: two-digit source indices in parameter names
+])
+def test_edge_shapes_match_oracle(epoch_counts, binaries, a1dot):
+    case = _multi_case(21, epoch_counts, binaries=binaries, a1dot=a1dot)
+    theta = case.sample_theta(333, seed=1)
+    want = _oracle_batch(case, theta)
+    scale = max(logl_scale(case.LoD_VLBI), 1.0)
+    for mode in ('fast', 'strict'):
+        like = case.likelihood(mode=mode)
+        for lanes in ((0, 1, 8, 32) if mode == 'fast' else (0,)):
+            got = like.log_likelihood_batch(theta, lanes=lanes)
+            err = logl_err(got, want, scale)
+            assert err.max() < LOGL_RTOL, (epoch_counts, mode, lanes, err.max())
+        like.close()
+
+
+def test_extreme_variance_tables_take_the_safe_path():
+    """Errors so small that a product of four variances would underflow: the library must
+    fall back to per-variance exponent extraction and still match the oracle."""
+    case = _multi_case(5, (40,), efac=True)
+    v = case.LoD_VLBI[0]
+    for k in ('errs', 'errs_random', 'errs_sys'):
+        v[k] = v[k] * 1e-45                    # variances ~1e-108: v^4 underflows a double
+    theta = case.sample_theta(64, seed=2)
+    want = _oracle_batch(case, theta)
+    like = case.likelihood()
+    got = like.log_likelihood_batch(theta)
+    assert np.isfinite(want).all()
+    assert (np.abs(got - want) / np.abs(want)).max() < 1e-9      # chi^2 ~ 1e90 dominates: pure relative check
+    like.close()

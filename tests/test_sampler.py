@@ -102,3 +102,39 @@ def test_config2_4096_walkers_step_on_gpu():
     assert 0.05 < s.acceptance_fraction < 0.95
     assert s.ncalls == 101
     like.close()
+
+
+@pytest.mark.gpu
+def test_fused_log_posterior_equals_prior_plus_likelihood():
+    """stn_logpost (one launch) == BoxPrior.log_prob + log_likelihood_batch, -inf mask included."""
+    case = synthetic.config3('dots')
+    like = case.likelihood()
+    keys = list(reversed(case.names))
+    limits = {}
+    for k in case.names:
+        lo, hi = case.box[k]
+        if k.startswith('incl'):
+            limits[k] = [0.1, 3.0, 'Sine']
+        elif k.startswith('mu_a'):
+            limits[k] = [case.truth[k], 1.5, 'Gaussian']
+        else:
+            limits[k] = [lo, hi, 'Uniform']
+    prior = BoxPrior(limits, {'sin_incl_limits_constraints': {'incl_0': [0.3, 0.999]}}, keys=keys)
+    theta = case.sample_theta(2048, seed=12, scale=1.15)[:, ::-1].copy()      # ~25 % fall outside the box
+    th = torch.from_numpy(theta).cuda()
+    fused = like.log_posterior_batch(th, prior).cpu().numpy()
+    lp = prior.log_prob(theta)
+    ll = like.log_likelihood_batch(theta, keys=keys)
+    want = np.where(np.isfinite(lp), lp + ll, -np.inf)
+    assert np.array_equal(np.isfinite(fused), np.isfinite(want))
+    assert 0.05 < np.isinf(fused).mean() < 0.95
+    m = np.isfinite(want)
+    assert (np.abs(fused[m] - want[m]) / np.maximum(np.abs(want[m]), 400.0)).max() < 1e-13
+    # the built-in sampler driven by the fused entry point
+    s = EnsembleSampler(256, case.n_params, lambda x: like.log_posterior_batch(x, prior), device='cuda:0', seed=4)
+    p0 = torch.from_numpy(case.sample_theta(256, seed=13, scale=0.05)[:, ::-1].copy()).cuda()
+    s.run(p0, 30)
+    assert 0.02 < s.acceptance_fraction < 0.98
+    with pytest.raises(TypeError):
+        like.log_posterior_batch(theta, prior)
+    like.close()
