@@ -132,8 +132,9 @@ def test_fused_log_posterior_equals_prior_plus_likelihood():
     assert (np.abs(fused[m] - want[m]) / np.maximum(np.abs(want[m]), 400.0)).max() < 1e-13
     # the built-in sampler driven by the fused entry point
     s = EnsembleSampler(256, case.n_params, lambda x: like.log_posterior_batch(x, prior), device='cuda:0', seed=4)
-    p0 = torch.from_numpy(case.sample_theta(256, seed=13, scale=0.05)[:, ::-1].copy()).cuda()
-    s.run(p0, 30)
+    half = np.array([0.5 * (case.box[k][1] - case.box[k][0]) for k in case.names])
+    p0 = case.truth_vector() + 0.02 * half * np.random.default_rng(13).standard_normal((256, case.n_params))
+    s.run(torch.from_numpy(p0[:, ::-1].copy()).cuda(), 30)
     assert 0.02 < s.acceptance_fraction < 0.98
     with pytest.raises(TypeError):
         like.log_posterior_batch(theta, prior)
