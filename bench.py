@@ -188,10 +188,10 @@ def run_ours(args, rank, local_rank, world):
     out = torch.empty(N, dtype=torch.float64, device=dev)
     sharded = ShardedLikelihood(like) if world > 1 else None
     gathered = torch.empty(N * world, dtype=torch.float64, device=dev) if world > 1 else None
-    lanes = ctx.auto_lanes(N * world)
+    plan = ctx.auto_plan(N * world)
 
     def step():
-        like.log_likelihood_batch(theta, out=out, lanes=lanes)
+        like.log_likelihood_batch(theta, out=out, plan=plan)
         if world > 1:
             dist.all_gather_into_tensor(gathered, out)
 
@@ -217,7 +217,7 @@ def run_ours(args, rank, local_rank, world):
     for _ in range(args.steps):
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         k0.record()
-        like.log_likelihood_batch(theta, out=out, lanes=lanes)
+        like.log_likelihood_batch(theta, out=out, plan=plan)
         k1.record()
         if world > 1:
             dist.all_gather_into_tensor(gathered, out)
@@ -235,12 +235,12 @@ def run_ours(args, rank, local_rank, world):
     out_host = torch.empty(N, dtype=torch.float64, pin_memory=True)
     th_np, out_np = theta_host.numpy(), out_host.numpy()
     for _ in range(2):
-        like.log_likelihood_batch(th_np, out=out_np, lanes=lanes)
+        like.log_likelihood_batch(th_np, out=out_np, plan=plan)
     sync_all()
     t0 = time.perf_counter()
     e2e_steps = max(2, min(args.steps, 5))
     for _ in range(e2e_steps):
-        like.log_likelihood_batch(th_np, out=out_np, lanes=lanes)      # synchronous: result is on the host
+        like.log_likelihood_batch(th_np, out=out_np, plan=plan)      # synchronous: result is on the host
     sync_all()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     same = bool(torch.equal(out_host.to(dev), out))

@@ -136,12 +136,16 @@ int stn_destroy(StnCtx* ctx);
 /* Batched log-likelihood, device buffers.
  * Replaces: Gaussianlikelihood.log_likelihood (simulate.py:362-384) evaluated for
  * n parameter vectors.  theta_dev: n vectors of P doubles in `layout` with leading
- * dimension ld; out_dev: n doubles.  lanes = 0 lets the library choose how many
- * lanes of a warp share one sample (1,2,4,...,32); pass an explicit value to make
- * results independent of how a batch is sharded.  Asynchronous on `stream`
- * (a cudaStream_t, NULL = default stream). */
+ * dimension ld; out_dev: n doubles.
+ * plan = 0 lets the library choose the execution plan from n; otherwise
+ * plan = lanes | (splits << 8): `lanes` (1,2,4,...,32) lanes of a warp share one sample,
+ * `splits` (1..number of 128-epoch chunks) CTAs share one tile of samples and their partial
+ * sums are added in a fixed order by a second small kernel.  The plan fixes the summation
+ * order, i.e. the result bits: pass the plan chosen for the WHOLE batch (stn_auto_plan) to
+ * make results independent of how a batch is sharded.  Asynchronous on `stream`
+ * (a cudaStream_t, NULL = default stream); one stream at a time per context. */
 int stn_loglike(StnCtx* ctx, const double* theta_dev, int64_t n, int64_t ld,
-                int layout, int mode, int lanes, double* out_dev, void* stream);
+                int layout, int mode, int plan, double* out_dev, void* stream);
 
 /* Installs (copies) the prior used by stn_logpost.  Replaces: priors.create_priors_given_limits_dict
  * (priors.py:344-366) evaluated per walker by bilby. */
@@ -150,13 +154,18 @@ int stn_set_prior(StnCtx* ctx, const StnPrior* prior);
 /* log prior + log likelihood for n vectors; -inf outside the prior's support.  Same
  * arguments as stn_loglike.  Requires stn_set_prior. */
 int stn_logpost(StnCtx* ctx, const double* theta_dev, int64_t n, int64_t ld,
-                int layout, int mode, int lanes, double* out_dev, void* stream);
+                int layout, int mode, int plan, double* out_dev, void* stream);
+
+/* sum over sources and epochs of ((obs - model)/sigma)^2 for n vectors, same arguments as
+ * stn_loglike.  Replaces: the chi-square of calculate_reduced_chi_square (simulate.py:290-301). */
+int stn_chisq(StnCtx* ctx, const double* theta_dev, int64_t n, int64_t ld,
+              int layout, int mode, int plan, double* out_dev, void* stream);
 
 /* Batched log-likelihood, HOST buffers: H2D copy, kernel(s), D2H copy, synchronised on return.
  * Large batches are cut into chunks whose copies overlap the kernels.  Pinned
  * buffers (stn_host_alloc) are copied at full PCIe rate. */
 int stn_loglike_host(StnCtx* ctx, const double* theta_host, int64_t n, int64_t ld,
-                     int layout, int mode, int lanes, double* out_host);
+                     int layout, int mode, int plan, double* out_host);
 
 /* Model positions of one source for n parameter vectors.
  * Replaces: positions() (positions.py:13-30) -> radec_dev[n][2E] = concat(ra[E], dec[E]) rad;
@@ -164,8 +173,8 @@ int stn_loglike_host(StnCtx* ctx, const double* theta_host, int64_t n, int64_t l
 int stn_model(StnCtx* ctx, int source, const double* theta_dev, int64_t n, int64_t ld,
               int layout, int mode, double* radec_dev, double* off_mas_dev, void* stream);
 
-/* Choice stn_loglike(lanes = 0) would make for a batch of n. */
-int stn_auto_lanes(StnCtx* ctx, int64_t n);
+/* The plan stn_loglike(plan = 0) would choose for a batch of n. */
+int stn_auto_plan(StnCtx* ctx, int64_t n);
 
 /* Number of kernel launches issued through this context so far. */
 int64_t stn_launch_count(StnCtx* ctx);
@@ -181,7 +190,7 @@ int stn_fp64_peak(int device, int iters, int reps, double* tflops, double* ms);
 /* Timing helper for bench.py: runs `steps` back-to-back stn_loglike launches on an
  * internal stream bracketed by CUDA events on that stream; returns total ms. */
 int stn_loglike_timed(StnCtx* ctx, const double* theta_dev, int64_t n, int64_t ld,
-                      int layout, int mode, int lanes, double* out_dev, int steps,
+                      int layout, int mode, int plan, double* out_dev, int steps,
                       double* total_ms);
 
 #ifdef __cplusplus

@@ -68,9 +68,10 @@ SYMBOLS = [
     ('stn_loglike', _int, [_vp, _vp, _i64, _i64, _int, _int, _int, _vp, _vp]),
     ('stn_set_prior', _int, [_vp, ctypes.POINTER(StnPrior)]),
     ('stn_logpost', _int, [_vp, _vp, _i64, _i64, _int, _int, _int, _vp, _vp]),
+    ('stn_chisq', _int, [_vp, _vp, _i64, _i64, _int, _int, _int, _vp, _vp]),
     ('stn_loglike_host', _int, [_vp, _vp, _i64, _i64, _int, _int, _int, _vp]),
     ('stn_model', _int, [_vp, _int, _vp, _i64, _i64, _int, _int, _vp, _vp, _vp]),
-    ('stn_auto_lanes', _int, [_vp, _i64]),
+    ('stn_auto_plan', _int, [_vp, _i64]),
     ('stn_launch_count', _i64, [_vp]),
     ('stn_host_alloc', _int, [ctypes.POINTER(_vp), _i64]),
     ('stn_host_free', _int, [_vp]),
@@ -114,6 +115,15 @@ def load(build_if_missing=True):
         fn.argtypes = argtypes
     _lib = lib
     return lib
+
+
+def make_plan(lanes=1, splits=1):
+    """plan = lanes | (splits << 8) (include/sterne_b200.h, stn_loglike)."""
+    return int(lanes) | (int(splits) << 8)
+
+
+def plan_parts(plan):
+    return plan & 0xff, (plan >> 8) & 0xffff
 
 
 def check(rc):

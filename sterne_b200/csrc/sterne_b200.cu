@@ -88,7 +88,8 @@ struct ChunkDev {
 
 struct ProbDev {
     int n_sources, n_params, n_chunks, n_a1dot, n_sini;
-    int n_prior, n_sinlim, pad0;      // n_prior = 0: likelihood only
+    int n_prior, n_sinlim;            // n_prior = 0: likelihood only
+    int out_chisq;                    // 1: write sum((res/sigma)^2) instead of log L (stn_chisq)
     double prior_const;               // sum of the priors' normalisation terms
     const int* prior_kind;
     const double* prior_a;
@@ -431,7 +432,8 @@ __device__ double prior_terms(const ProbDev& P, const double* __restrict__ theta
 template <int R, int L>
 __global__ void __launch_bounds__(kThreads, (R > 2 ? 1 : 2))
 stn_loglike_fast_kernel(const ProbDev P, const double* __restrict__ theta, const int64_t N,
-                        const int64_t ld, const int layout, double* __restrict__ out) {
+                        const int64_t ld, const int layout, double* __restrict__ out,
+                        double* __restrict__ partial) {
     __shared__ __align__(128) double stage[kStages][kChunk * STN_FAST_ROW];
     __shared__ __align__(8) uint64_t full[kStages];
 
@@ -456,8 +458,13 @@ stn_loglike_fast_kernel(const ProbDev P, const double* __restrict__ theta, const
         mbar_fence_init();
     }
     __syncthreads();
-    if (tid == 0 && P.n_chunks > 0) {
-        const ChunkDev c0 = P.chunks[0];
+    // gridDim.y CTAs share one tile of samples: CTA k walks chunks [c_begin, c_end) and the
+    // per-split partial sums are added in split order by stn_reduce_splits_kernel.
+    const int K = (int)gridDim.y;
+    const int c_begin = (int)(((int64_t)P.n_chunks * blockIdx.y) / K);
+    const int c_end = (int)(((int64_t)P.n_chunks * (blockIdx.y + 1)) / K);
+    if (tid == 0 && c_begin < c_end) {
+        const ChunkDev c0 = P.chunks[c_begin];
         stage_fill(stage[0], c0.rows, c0.n_epochs, &full[0]);
     }
 
@@ -468,16 +475,19 @@ stn_loglike_fast_kernel(const ProbDev P, const double* __restrict__ theta, const
 #pragma unroll
     for (int r = 0; r < R; ++r) logl[r] = 0.0;
 
-    for (int c = 0; c < P.n_chunks; ++c) {
+    for (int c = c_begin; c < c_end; ++c) {
         const ChunkDev ck = P.chunks[c];
-        if (tid == 0 && c + 1 < P.n_chunks) {
-            // stage (c+1)&1 was last read in iteration c-1; the __syncthreads that ended it
+        const int it = c - c_begin;                      // stage = it & 1, phase parity = (it >> 1) & 1
+        if (tid == 0 && c + 1 < c_end) {
+            // stage (it+1)&1 was last read in iteration it-1; the __syncthreads that ended it
             // ordered those reads before this refill.
             const ChunkDev nx = P.chunks[c + 1];
-            stage_fill(stage[(c + 1) & 1], nx.rows, nx.n_epochs, &full[(c + 1) & 1]);
+            stage_fill(stage[(it + 1) & 1], nx.rows, nx.n_epochs, &full[(it + 1) & 1]);
         }
         const SrcDev& S = P.src[ck.source];
-        if (ck.flags & kFirst) {
+        const bool first = (ck.flags & kFirst) || c == c_begin;   // (re)start this source's sums
+        const bool last = (ck.flags & kLast) || c == c_end - 1;   // fold them into log L
+        if (first) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const Params p = load_params(S, theta, nidx[r], ld, layout);
@@ -488,12 +498,12 @@ stn_loglike_fast_kernel(const ProbDev P, const double* __restrict__ theta, const
                 acc[r].esum = 0;
             }
         }
-        mbar_wait(&full[c & 1], (uint32_t)((c >> 1) & 1));
-        const double* rows = stage[c & 1];
+        mbar_wait(&full[it & 1], (uint32_t)((it >> 1) & 1));
+        const double* rows = stage[it & 1];
         const bool ef = S.efac_on != 0;
         const bool bin = S.binary != 0;
         const bool grouped = S.grouped != 0;
-        if (ck.flags & kFirst) nsplit = 0;
+        if (first) nsplit = 0;
         if (!ef && !bin) epoch_loop<R, L, false, false, false>(rows, ck.n_epochs, sub, cf, acc);
         else if (!ef && bin) epoch_loop<R, L, false, true, false>(rows, ck.n_epochs, sub, cf, acc);
         else if (ef && !bin && grouped) nsplit += epoch_loop<R, L, true, false, false>(rows, ck.n_epochs, sub, cf, acc);
@@ -501,7 +511,7 @@ stn_loglike_fast_kernel(const ProbDev P, const double* __restrict__ theta, const
         else if (ef && !bin) nsplit += epoch_loop<R, L, true, false, true>(rows, ck.n_epochs, sub, cf, acc);
         else nsplit += epoch_loop<R, L, true, true, true>(rows, ck.n_epochs, sub, cf, acc);
 
-        if (ck.flags & kLast) {
+        if (last) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 // log_p += -0.5*sum((res/errs)^2); log_p += -sum(log(errs))  (simulate.py:370-371)
@@ -512,24 +522,52 @@ stn_loglike_fast_kernel(const ProbDev P, const double* __restrict__ theta, const
                     const double part = log(acc[r].prod) + (double)(acc[r].esum - 1023 * nsplit) * STN_LN2;
                     logdet = -0.5 * group_sum<L>(part);
                 } else {
-                    logdet = S.neg_sum_log_err;
+                    // host constant, counted once: by the split that holds the source's last chunk
+                    logdet = (ck.flags & kLast) ? S.neg_sum_log_err : 0.0;
                 }
-                logl[r] += -0.5 * chi;
-                logl[r] += logdet;
+                if (P.out_chisq) {
+                    logl[r] += chi;
+                } else {
+                    logl[r] += -0.5 * chi;
+                    logl[r] += logdet;
+                }
             }
         }
         __syncthreads();
     }
 
+    if (K > 1) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (valid[r] && sub == 0) partial[(int64_t)blockIdx.y * N + nidx[r]] = logl[r];
+        return;
+    }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        if (P.n_a1dot > 0 || P.n_sini > 0) logl[r] += constraint_terms(P, theta, nidx[r], ld, layout);
-        if (P.n_prior > 0) {
+        if (!P.out_chisq && (P.n_a1dot > 0 || P.n_sini > 0)) logl[r] += constraint_terms(P, theta, nidx[r], ld, layout);
+        if (!P.out_chisq && P.n_prior > 0) {
             const double lp = prior_terms(P, theta, nidx[r], ld, layout);
             logl[r] = (lp == -CUDART_INF) ? lp : logl[r] + lp;
         }
         if (valid[r] && sub == 0) out[nidx[r]] = logl[r];
     }
+}
+
+// second pass of a split launch: partial sums in split order, then the per-vector terms
+__global__ void __launch_bounds__(kThreads)
+stn_reduce_splits_kernel(const ProbDev P, const double* __restrict__ theta, const int64_t N, const int64_t ld,
+                         const int layout, const int K, const double* __restrict__ partial,
+                         double* __restrict__ out) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    double logl = partial[n];
+    for (int k = 1; k < K; ++k) logl += partial[(int64_t)k * N + n];
+    if (!P.out_chisq && (P.n_a1dot > 0 || P.n_sini > 0)) logl += constraint_terms(P, theta, n, ld, layout);
+    if (!P.out_chisq && P.n_prior > 0) {
+        const double lp = prior_terms(P, theta, n, ld, layout);
+        logl = (lp == -CUDART_INF) ? lp : logl + lp;
+    }
+    out[n] = logl;
 }
 
 // ---------------------------------------------------------------------------------
@@ -630,11 +668,15 @@ stn_loglike_strict_kernel(const ProbDev P, const double* __restrict__ theta, con
                 chi = __dadd_rn(chi, __dmul_rn(z, z));
             }
         }
-        logl = __dadd_rn(logl, __dmul_rn(-0.5, chi));
-        logl = __dadd_rn(logl, S.efac_on ? -slog : S.neg_sum_log_err);
+        if (P.out_chisq) {
+            logl = __dadd_rn(logl, chi);               // chi_sq += np.sum((res/errs_new)**2)  simulate.py:297
+        } else {
+            logl = __dadd_rn(logl, __dmul_rn(-0.5, chi));
+            logl = __dadd_rn(logl, S.efac_on ? -slog : S.neg_sum_log_err);
+        }
     }
-    if (P.n_a1dot > 0 || P.n_sini > 0) logl += constraint_terms(P, theta, n, ld, layout);
-    if (P.n_prior > 0) {
+    if (!P.out_chisq && (P.n_a1dot > 0 || P.n_sini > 0)) logl += constraint_terms(P, theta, n, ld, layout);
+    if (!P.out_chisq && P.n_prior > 0) {
         const double lp = prior_terms(P, theta, n, ld, layout);
         logl = (lp == -CUDART_INF) ? lp : logl + lp;
     }
@@ -732,6 +774,8 @@ struct StnCtx {
     bool has_prior = false;
     std::vector<void*> prior_allocs;
     bool efac_heavy = false;            // at least half of the epochs belong to EFAC sources
+    double* scratch[3] = {nullptr, nullptr, nullptr};   // split partial sums: [0] device API, [1],[2] host streams
+    int64_t scratch_elems[3] = {0, 0, 0};
     int64_t launches = 0;
     // *_host staging
     cudaStream_t streams[2] = {nullptr, nullptr};
@@ -754,33 +798,91 @@ int upload(StnCtx* ctx, const T* host, size_t count, const T** dev_out) {
     return STN_OK;
 }
 
-int pick_lanes(const StnCtx* ctx, int64_t n) {
-    // enough threads for ~2 CTAs on every SM; never more lanes than a quarter of the
-    // longest epoch list (the prologue is replicated on every lane)
-    const int64_t target = (int64_t)2 * ctx->sm_count * kThreads;
-    int cap = 1;
-    while (cap < 32 && cap * 8 <= ctx->max_epochs) cap *= 2;
+// ---- execution plan -------------------------------------------------------------------
+// plan = lanes | (splits << 8).  lanes: lanes of a warp sharing one sample (epochs of a chunk
+// interleaved over them); splits: CTAs sharing one tile of samples (the chunk list cut into
+// contiguous ranges).  Both change the summation order, i.e. result bits, which is why the
+// plan is explicit in the ABI; samples per thread (R) never does.
+inline int plan_lanes(int plan) { return plan & 0xff; }
+inline int plan_splits(int plan) { return (plan >> 8) & 0xffff; }
+inline int make_plan(int lanes, int splits) { return lanes | (splits << 8); }
+
+int big_R(const StnCtx* ctx) { return ctx->efac_heavy ? STN_RBIG_EFAC : STN_RBIG; }
+
+// R used for a batch of n with `splits` CTAs per tile: the big R once its tiles fill the SMs
+int choose_R(const StnCtx* ctx, int64_t n, int lanes, int splits) {
+    if (lanes != 1) return 1;
+    const int R = big_R(ctx);
+    const int64_t slots = (int64_t)ctx->sm_count * (R > 2 ? 1 : 2);
+    const int64_t tiles = (n + (int64_t)kThreads * R - 1) / ((int64_t)kThreads * R);
+    return tiles * splits >= 2 * slots ? R : 1;
+}
+
+int pick_plan(const StnCtx* ctx, int64_t n) {
+    if (n <= 0) return make_plan(1, 1);
+    const int T = ctx->prob.n_chunks;
+    const int R = big_R(ctx);
+    const int64_t slots_big = (int64_t)ctx->sm_count * (R > 2 ? 1 : 2);
+    const int64_t tiles_big = (n + (int64_t)kThreads * R - 1) / ((int64_t)kThreads * R);
+    if (tiles_big >= 8 * slots_big) return make_plan(1, 1);          // >= 8 waves: no split needed
+    // choose the number of splits that wastes the least of the last wave, given the tile count
+    auto eff = [&](int64_t tiles, int64_t slots, int K) {
+        const int64_t ctas = tiles * K;
+        const int64_t waves = (ctas + slots - 1) / slots;
+        const double fill = (double)ctas / (double)(waves * slots);
+        const int per = (T + K - 1) / K;                              // chunks of the longest split
+        const double balance = (double)T / (double)((int64_t)per * K);
+        return fill * balance;
+    };
+    if (tiles_big * (int64_t)T >= 2 * slots_big) {                    // the big-R kernel can fill the GPU
+        int bestK = 1;
+        double best = eff(tiles_big, slots_big, 1);
+        for (int K = 2; K <= T && K <= 64; ++K) {
+            if (tiles_big * K < 2 * slots_big && K < T) continue;
+            const double e = eff(tiles_big, slots_big, K);
+            if (e > best * 1.02) { best = e; bestK = K; }
+            if (tiles_big * K >= 8 * slots_big) break;
+        }
+        if (tiles_big * bestK >= 2 * slots_big) return make_plan(1, bestK);
+    }
+    // small batches: one sample per thread, as many splits as there are chunks allow, then lanes
+    const int64_t slots = (int64_t)ctx->sm_count * 2;
+    const int64_t tiles = (n + kThreads - 1) / kThreads;
+    int K = 1;
+    while (K < T && K < 64 && tiles * K < 2 * slots) ++K;
+    int cap = 1;                                                       // lanes never outnumber epochs/8
+    while (cap < 32 && cap * 8 <= ctx->max_epochs && cap * 8 <= kChunk) cap *= 2;
     int L = 1;
-    while (L < cap && n * L < target) L *= 2;
-    return L;
+    while (L < cap && ((n * L + kThreads - 1) / kThreads) * K < 2 * slots) L *= 2;
+    return make_plan(L, K);
 }
 
 template <int R, int L>
 int launch_fast(StnCtx* ctx, const ProbDev& prob, const double* theta, int64_t n, int64_t ld, int layout,
-                double* out, cudaStream_t st) {
+                double* out, cudaStream_t st, int splits, double* partial) {
     constexpr int per_cta = (kThreads / L) * R;
     const int64_t grid = (n + per_cta - 1) / per_cta;
     if (grid > 0x7fffffffLL) return fail(STN_ERR_INVALID, "batch too large for one launch");
-    stn_loglike_fast_kernel<R, L><<<(unsigned)grid, kThreads, 0, st>>>(prob, theta, n, ld, layout, out);
+    dim3 g((unsigned)grid, (unsigned)splits, 1);
+    stn_loglike_fast_kernel<R, L><<<g, kThreads, 0, st>>>(prob, theta, n, ld, layout, out, partial);
     STN_CUDA(cudaGetLastError());
     ctx->launches++;
+    if (splits > 1) {
+        const int64_t rg = (n + kThreads - 1) / kThreads;
+        stn_reduce_splits_kernel<<<(unsigned)rg, kThreads, 0, st>>>(prob, theta, n, ld, layout, splits, partial, out);
+        STN_CUDA(cudaGetLastError());
+        ctx->launches++;
+    }
     return STN_OK;
 }
 
+// scratch_slot: 0 for the device-buffer API, 1/2 for the two streams of the host API
 int launch_loglike(StnCtx* ctx, const double* theta, int64_t n, int64_t ld, int layout, int mode,
-                   int lanes, double* out, cudaStream_t st, bool with_prior = false) {
+                   int plan, double* out, cudaStream_t st, int what = 0, int scratch_slot = 0) {
+    // what: 0 = log L, 1 = log prior + log L, 2 = chi-square
     if (n == 0) return STN_OK;
-    const ProbDev& prob = with_prior ? ctx->prior_prob : ctx->prob;
+    ProbDev prob = what == 1 ? ctx->prior_prob : ctx->prob;
+    prob.out_chisq = what == 2 ? 1 : 0;
     if (mode == STN_MODE_STRICT) {
         const int64_t grid = (n + kThreads - 1) / kThreads;
         stn_loglike_strict_kernel<<<(unsigned)grid, kThreads, 0, st>>>(prob, theta, n, ld, layout, out);
@@ -788,21 +890,44 @@ int launch_loglike(StnCtx* ctx, const double* theta, int64_t n, int64_t ld, int 
         ctx->launches++;
         return STN_OK;
     }
-    if (lanes == 0) lanes = pick_lanes(ctx, n);
+    if (plan == 0) plan = pick_plan(ctx, n);
+    const int lanes = plan_lanes(plan);
+    int splits = plan_splits(plan);
+    if (splits == 0) splits = 1;                                   // a bare lanes value is a valid plan
+    if (splits > ctx->prob.n_chunks && ctx->prob.n_chunks > 0)
+        return fail(STN_ERR_INVALID, "plan asks for %d splits but the problem has %d chunks", splits,
+                    ctx->prob.n_chunks);
+    if (splits > 65535) return fail(STN_ERR_INVALID, "too many splits");
+    double* partial = nullptr;
+    if (splits > 1) {
+        const int64_t need = (int64_t)splits * n;
+        if (ctx->scratch_elems[scratch_slot] < need) {
+            if (ctx->scratch[scratch_slot]) {
+                STN_CUDA(cudaStreamSynchronize(st));
+                STN_CUDA(cudaFree(ctx->scratch[scratch_slot]));
+                ctx->scratch[scratch_slot] = nullptr;
+                ctx->scratch_elems[scratch_slot] = 0;
+            }
+            STN_CUDA(cudaMalloc(&ctx->scratch[scratch_slot], (size_t)need * sizeof(double)));
+            ctx->scratch_elems[scratch_slot] = need;
+        }
+        partial = ctx->scratch[scratch_slot];
+    }
+    const int R = choose_R(ctx, n, lanes, splits);
+#define STN_GO(RR, LL) return launch_fast<RR, LL>(ctx, prob, theta, n, ld, layout, out, st, splits, partial)
     switch (lanes) {
         case 1:
-            // R only changes how samples map to threads, never a result bit
-            if (n >= (int64_t)4 * ctx->sm_count * kThreads)
-                return ctx->efac_heavy ? launch_fast<STN_RBIG_EFAC, 1>(ctx, prob, theta, n, ld, layout, out, st)
-                                       : launch_fast<STN_RBIG, 1>(ctx, prob, theta, n, ld, layout, out, st);
-            return launch_fast<1, 1>(ctx, prob, theta, n, ld, layout, out, st);
-        case 2: return launch_fast<1, 2>(ctx, prob, theta, n, ld, layout, out, st);
-        case 4: return launch_fast<1, 4>(ctx, prob, theta, n, ld, layout, out, st);
-        case 8: return launch_fast<1, 8>(ctx, prob, theta, n, ld, layout, out, st);
-        case 16: return launch_fast<1, 16>(ctx, prob, theta, n, ld, layout, out, st);
-        case 32: return launch_fast<1, 32>(ctx, prob, theta, n, ld, layout, out, st);
-        default: return fail(STN_ERR_INVALID, "lanes must be 0 or a power of two <= 32 (got %d)", lanes);
+            if (R == STN_RBIG_EFAC && STN_RBIG_EFAC != STN_RBIG) STN_GO(STN_RBIG_EFAC, 1);
+            if (R == STN_RBIG) STN_GO(STN_RBIG, 1);
+            STN_GO(1, 1);
+        case 2: STN_GO(1, 2);
+        case 4: STN_GO(1, 4);
+        case 8: STN_GO(1, 8);
+        case 16: STN_GO(1, 16);
+        case 32: STN_GO(1, 32);
+        default: return fail(STN_ERR_INVALID, "plan lanes must be a power of two <= 32 (got %d)", lanes);
     }
+#undef STN_GO
 }
 
 int check_call(StnCtx* ctx, const void* theta, int64_t n, int64_t ld, int layout, int mode,
@@ -945,6 +1070,8 @@ int stn_destroy(StnCtx* ctx) {
     cudaSetDevice(ctx->device);
     for (void* p : ctx->dev_allocs) cudaFree(p);
     for (void* p : ctx->prior_allocs) cudaFree(p);
+    for (int i = 0; i < 3; ++i)
+        if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     for (int i = 0; i < 2; ++i) {
         if (ctx->stage_theta[i]) cudaFree(ctx->stage_theta[i]);
         if (ctx->stage_out[i]) cudaFree(ctx->stage_out[i]);
@@ -955,19 +1082,19 @@ int stn_destroy(StnCtx* ctx) {
     return STN_OK;
 }
 
-int stn_auto_lanes(StnCtx* ctx, int64_t n) {
+int stn_auto_plan(StnCtx* ctx, int64_t n) {
     if (!ctx) return fail(STN_ERR_INVALID, "null context");
-    return pick_lanes(ctx, n);
+    return pick_plan(ctx, n);
 }
 
 int64_t stn_launch_count(StnCtx* ctx) { return ctx ? ctx->launches : 0; }
 
 int stn_loglike(StnCtx* ctx, const double* theta_dev, int64_t n, int64_t ld, int layout, int mode,
-                int lanes, double* out_dev, void* stream) {
+                int plan, double* out_dev, void* stream) {
     int rc = check_call(ctx, theta_dev, n, ld, layout, mode, out_dev);
     if (rc) return rc;
     STN_CUDA(cudaSetDevice(ctx->device));
-    return launch_loglike(ctx, theta_dev, n, ld, layout, mode, lanes, out_dev, static_cast<cudaStream_t>(stream));
+    return launch_loglike(ctx, theta_dev, n, ld, layout, mode, plan, out_dev, static_cast<cudaStream_t>(stream));
 }
 
 int stn_set_prior(StnCtx* ctx, const StnPrior* pr) {
@@ -1002,6 +1129,8 @@ int stn_set_prior(StnCtx* ctx, const StnPrior* pr) {
     STN_CUDA(cudaSetDevice(ctx->device));
     STN_CUDA(cudaDeviceSynchronize());                 // no launch may still read the old prior
     for (void* p : ctx->prior_allocs) cudaFree(p);
+    for (int i = 0; i < 3; ++i)
+        if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     ctx->prior_allocs.clear();
     ctx->has_prior = false;
     ProbDev P = ctx->prob;
@@ -1026,17 +1155,26 @@ int stn_set_prior(StnCtx* ctx, const StnPrior* pr) {
 }
 
 int stn_logpost(StnCtx* ctx, const double* theta_dev, int64_t n, int64_t ld, int layout, int mode,
-                int lanes, double* out_dev, void* stream) {
+                int plan, double* out_dev, void* stream) {
     int rc = check_call(ctx, theta_dev, n, ld, layout, mode, out_dev);
     if (rc) return rc;
     if (!ctx->has_prior) return fail(STN_ERR_INVALID, "stn_logpost needs stn_set_prior first");
     STN_CUDA(cudaSetDevice(ctx->device));
-    return launch_loglike(ctx, theta_dev, n, ld, layout, mode, lanes, out_dev, static_cast<cudaStream_t>(stream),
-                          true);
+    return launch_loglike(ctx, theta_dev, n, ld, layout, mode, plan, out_dev, static_cast<cudaStream_t>(stream),
+                          1);
+}
+
+int stn_chisq(StnCtx* ctx, const double* theta_dev, int64_t n, int64_t ld, int layout, int mode,
+              int plan, double* out_dev, void* stream) {
+    int rc = check_call(ctx, theta_dev, n, ld, layout, mode, out_dev);
+    if (rc) return rc;
+    STN_CUDA(cudaSetDevice(ctx->device));
+    return launch_loglike(ctx, theta_dev, n, ld, layout, mode, plan, out_dev, static_cast<cudaStream_t>(stream),
+                          2);
 }
 
 int stn_loglike_timed(StnCtx* ctx, const double* theta_dev, int64_t n, int64_t ld, int layout,
-                      int mode, int lanes, double* out_dev, int steps, double* total_ms) {
+                      int mode, int plan, double* out_dev, int steps, double* total_ms) {
     int rc = check_call(ctx, theta_dev, n, ld, layout, mode, out_dev);
     if (rc) return rc;
     if (steps <= 0 || !total_ms) return fail(STN_ERR_INVALID, "bad steps / null total_ms");
@@ -1048,7 +1186,7 @@ int stn_loglike_timed(StnCtx* ctx, const double* theta_dev, int64_t n, int64_t l
     STN_CUDA(cudaDeviceSynchronize());
     STN_CUDA(cudaEventRecord(e0, ctx->timing_stream));
     for (int i = 0; i < steps; ++i) {
-        rc = launch_loglike(ctx, theta_dev, n, ld, layout, mode, lanes, out_dev, ctx->timing_stream);
+        rc = launch_loglike(ctx, theta_dev, n, ld, layout, mode, plan, out_dev, ctx->timing_stream);
         if (rc) return rc;
     }
     STN_CUDA(cudaEventRecord(e1, ctx->timing_stream));
@@ -1062,7 +1200,7 @@ int stn_loglike_timed(StnCtx* ctx, const double* theta_dev, int64_t n, int64_t l
 }
 
 int stn_loglike_host(StnCtx* ctx, const double* theta_host, int64_t n, int64_t ld, int layout,
-                     int mode, int lanes, double* out_host) {
+                     int mode, int plan, double* out_host) {
     int rc = check_call(ctx, theta_host, n, ld, layout, mode, out_host);
     if (rc) return rc;
     if (n == 0) return STN_OK;
@@ -1087,7 +1225,7 @@ int stn_loglike_host(StnCtx* ctx, const double* theta_host, int64_t n, int64_t l
     }
     for (int i = 0; i < 2; ++i)
         if (!ctx->streams[i]) STN_CUDA(cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking));
-    if (mode == STN_MODE_FAST && lanes == 0) lanes = pick_lanes(ctx, n);   // from the whole batch
+    if (mode == STN_MODE_FAST && plan == 0) plan = pick_plan(ctx, n);    // from the whole batch
     int k = 0;
     for (int64_t lo = 0; lo < n; lo += rows, ++k) {
         const int64_t m = (n - lo) < rows ? (n - lo) : rows;
@@ -1111,7 +1249,7 @@ int stn_loglike_host(StnCtx* ctx, const double* theta_host, int64_t n, int64_t l
                                        cudaMemcpyHostToDevice, st));
             dld = m;
         }
-        rc = launch_loglike(ctx, dth, m, dld, layout, mode, lanes, dout, st);
+        rc = launch_loglike(ctx, dth, m, dld, layout, mode, plan, dout, st, 0, 1 + (k & 1));
         if (rc) return rc;
         STN_CUDA(cudaMemcpyAsync(out_host + lo, dout, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
     }

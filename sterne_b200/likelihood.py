@@ -62,12 +62,12 @@ class Gaussianlikelihood(_LikelihoodBase):
     Positional arguments are the reference's (simulate.py:326).  `positions` is accepted
     for signature compatibility and ignored: the model is the device kernel.
     Keyword-only extras: earth_provider / earth_xyz (ephemeris.py), device, mode
-    ('fast' | 'strict'), lanes (0 = automatic).
+    ('fast' | 'strict'), plan (0 = automatic; see stn_loglike in include/sterne_b200.h).
     """
 
     def __init__(self, refepoch, list_of_dict_timing, list_of_dict_VLBI, shares, positions=None,
                  DoD_additional_constraints=None, a1dot_constraints=False, *, earth_provider=None,
-                 earth_xyz=None, device=0, mode='fast', lanes=0):
+                 earth_xyz=None, device=0, mode='fast', plan=0):
         self.refepoch = refepoch
         self.LoD_VLBI = list_of_dict_VLBI
         self.LoD_timing = list_of_dict_timing
@@ -81,7 +81,7 @@ class Gaussianlikelihood(_LikelihoodBase):
         self.a1dot_constraints = a1dot_constraints
         self.device = int(device)
         self.mode = _lib.MODES[mode]
-        self.lanes = int(lanes)
+        self.plan = int(plan)
         needs_px = any(int(v) >= 0 for v in shares[7])
         self._provider = _resolve_provider(earth_provider) if (needs_px and earth_xyz is None) else earth_provider
         self._earth_xyz = earth_xyz
@@ -125,7 +125,7 @@ class Gaussianlikelihood(_LikelihoodBase):
         return float(self.log_likelihood_batch(theta)[0])
 
     # ------------------------------------------------------------- batched API
-    def log_likelihood_batch(self, theta, keys=None, out=None, layout='aos', mode=None, lanes=None):
+    def log_likelihood_batch(self, theta, keys=None, out=None, layout='aos', mode=None, plan=None):
         """log-L of N parameter vectors.
 
         theta : (N, P) float64, numpy array or CUDA torch tensor (layout='aos'), or
@@ -135,12 +135,12 @@ class Gaussianlikelihood(_LikelihoodBase):
         ctx = self._context(keys)
         P = ctx.problem.n_params
         mode = self.mode if mode is None else _lib.MODES[mode]
-        lanes = self.lanes if lanes is None else int(lanes)
+        plan = self.plan if plan is None else int(plan)
         lay = _lib.LAYOUT_AOS if layout == 'aos' else _lib.LAYOUT_SOA
         if _is_torch_tensor(theta):
             import torch
             if not theta.is_cuda:
-                return torch.from_numpy(self.log_likelihood_batch(theta.numpy(), keys, None, layout, mode, lanes))
+                return torch.from_numpy(self.log_likelihood_batch(theta.numpy(), keys, None, layout, mode, plan))
             if theta.dtype != torch.float64 or theta.dim() != 2:
                 raise TypeError('theta must be a 2-D float64 tensor')
             if theta.device.index != self.device:
@@ -152,7 +152,7 @@ class Gaussianlikelihood(_LikelihoodBase):
             if out is None:
                 out = torch.empty(n, dtype=torch.float64, device=theta.device)
             stream = torch.cuda.current_stream(theta.device).cuda_stream
-            ctx.loglike_ptr(theta.data_ptr(), n, ld, lay, mode, lanes, out.data_ptr(), stream)
+            ctx.loglike_ptr(theta.data_ptr(), n, ld, lay, mode, plan, out.data_ptr(), stream)
             return out
         theta = np.asarray(theta, dtype=np.float64)
         if theta.ndim != 2:
@@ -162,10 +162,10 @@ class Gaussianlikelihood(_LikelihoodBase):
         n, ld = self._shape(theta.shape, theta.strides[0] // 8, lay, P)
         if out is None:
             out = np.empty(n, dtype=np.float64)
-        ctx.loglike_host_ptr(theta.ctypes.data, n, ld, lay, mode, lanes, out.ctypes.data)
+        ctx.loglike_host_ptr(theta.ctypes.data, n, ld, lay, mode, plan, out.ctypes.data)
         return out
 
-    def log_posterior_batch(self, theta, prior, out=None, mode=None, lanes=None):
+    def log_posterior_batch(self, theta, prior, out=None, mode=None, plan=None):
         """log prior + log L of N vectors in ONE launch (stn_logpost); -inf outside the prior's
         support.  theta: (N, P) float64 CUDA tensor whose columns follow prior.keys
         (sampler.BoxPrior).  Returns a CUDA tensor."""
@@ -181,13 +181,37 @@ class Gaussianlikelihood(_LikelihoodBase):
         if theta.stride(1) != 1:
             theta = theta.contiguous()
         mode = self.mode if mode is None else _lib.MODES[mode]
-        lanes = self.lanes if lanes is None else int(lanes)
+        plan = self.plan if plan is None else int(plan)
         n, ld = self._shape(theta.shape, theta.stride(0), _lib.LAYOUT_AOS, ctx.problem.n_params)
         if out is None:
             out = torch.empty(n, dtype=torch.float64, device=theta.device)
         stream = torch.cuda.current_stream(theta.device).cuda_stream
-        ctx.logpost_ptr(theta.data_ptr(), n, ld, _lib.LAYOUT_AOS, mode, lanes, out.data_ptr(), stream)
+        ctx.logpost_ptr(theta.data_ptr(), n, ld, _lib.LAYOUT_AOS, mode, plan, out.data_ptr(), stream)
         return out
+
+    def chi_square_batch(self, theta, keys=None, mode=None, plan=None):
+        """sum((obs - model)/sigma)^2 over all sources and epochs for N vectors (simulate.py:297)."""
+        import torch
+        ctx = self._context(keys)
+        dev = torch.device('cuda', self.device)
+        was_numpy = not _is_torch_tensor(theta)
+        th = torch.as_tensor(np.asarray(theta, dtype=np.float64) if was_numpy else theta).to(dev, torch.float64).contiguous()
+        n, ld = self._shape(th.shape, th.stride(0), _lib.LAYOUT_AOS, ctx.problem.n_params)
+        out = torch.empty(n, dtype=torch.float64, device=dev)
+        mode = self.mode if mode is None else _lib.MODES[mode]
+        plan = self.plan if plan is None else int(plan)
+        ctx.chisq_ptr(th.data_ptr(), n, ld, _lib.LAYOUT_AOS, mode, plan, out.data_ptr(),
+                      torch.cuda.current_stream(dev).cuda_stream)
+        return out.cpu().numpy() if was_numpy else out
+
+    def calculate_reduced_chi_square(self, dict_median):
+        """(chi_sq, reduced chi_sq) at one parameter dict, as simulate.calculate_reduced_chi_square
+        (simulate.py:290-301): DoF = 2 * total epochs - number of parameters."""
+        names = self.parameter_names
+        theta = np.array([[float(dict_median[k]) for k in names]], dtype=np.float64)
+        chi_sq = float(self.chi_square_batch(theta)[0])
+        n_obs = 2 * sum(len(v['epochs']) for v in self.LoD_VLBI)
+        return chi_sq, chi_sq / (n_obs - len(dict_median))
 
     @staticmethod
     def _shape(shape, stride0, lay, P):

@@ -202,8 +202,8 @@ class DeviceContext(object):
             pass
 
     # ---- raw entry points (pointers are integers: tensor.data_ptr() / ndarray.ctypes.data)
-    def loglike_ptr(self, theta_ptr, n, ld, layout, mode, lanes, out_ptr, stream=0):
-        _lib.check(self.lib.stn_loglike(self.handle, theta_ptr, n, ld, layout, mode, lanes, out_ptr, stream))
+    def loglike_ptr(self, theta_ptr, n, ld, layout, mode, plan, out_ptr, stream=0):
+        _lib.check(self.lib.stn_loglike(self.handle, theta_ptr, n, ld, layout, mode, plan, out_ptr, stream))
 
     def set_prior(self, prior):
         """prior: sampler.BoxPrior whose keys are this context's column order."""
@@ -229,25 +229,29 @@ class DeviceContext(object):
         _lib.check(self.lib.stn_set_prior(self.handle, ctypes.byref(pr)))
         self.prior = prior
 
-    def logpost_ptr(self, theta_ptr, n, ld, layout, mode, lanes, out_ptr, stream=0):
-        _lib.check(self.lib.stn_logpost(self.handle, theta_ptr, n, ld, layout, mode, lanes, out_ptr, stream))
+    def logpost_ptr(self, theta_ptr, n, ld, layout, mode, plan, out_ptr, stream=0):
+        _lib.check(self.lib.stn_logpost(self.handle, theta_ptr, n, ld, layout, mode, plan, out_ptr, stream))
 
-    def loglike_host_ptr(self, theta_ptr, n, ld, layout, mode, lanes, out_ptr):
-        _lib.check(self.lib.stn_loglike_host(self.handle, theta_ptr, n, ld, layout, mode, lanes, out_ptr))
+    def chisq_ptr(self, theta_ptr, n, ld, layout, mode, plan, out_ptr, stream=0):
+        _lib.check(self.lib.stn_chisq(self.handle, theta_ptr, n, ld, layout, mode, plan, out_ptr, stream))
+
+    def loglike_host_ptr(self, theta_ptr, n, ld, layout, mode, plan, out_ptr):
+        _lib.check(self.lib.stn_loglike_host(self.handle, theta_ptr, n, ld, layout, mode, plan, out_ptr))
 
     def model_ptr(self, source, theta_ptr, n, ld, layout, mode, radec_ptr, off_ptr, stream=0):
         _lib.check(self.lib.stn_model(self.handle, source, theta_ptr, n, ld, layout, mode, radec_ptr,
                                       off_ptr, stream))
 
-    def auto_lanes(self, n):
-        return int(self.lib.stn_auto_lanes(self.handle, n))
+    def auto_plan(self, n):
+        """Execution plan the library would choose for a batch of n (lanes | splits << 8)."""
+        return int(self.lib.stn_auto_plan(self.handle, n))
 
     def launch_count(self):
         return int(self.lib.stn_launch_count(self.handle))
 
-    def loglike_timed(self, theta_ptr, n, ld, layout, mode, lanes, out_ptr, steps):
+    def loglike_timed(self, theta_ptr, n, ld, layout, mode, plan, out_ptr, steps):
         ms = ctypes.c_double()
-        _lib.check(self.lib.stn_loglike_timed(self.handle, theta_ptr, n, ld, layout, mode, lanes, out_ptr,
+        _lib.check(self.lib.stn_loglike_timed(self.handle, theta_ptr, n, ld, layout, mode, plan, out_ptr,
                                               steps, ctypes.byref(ms)))
         return ms.value
 

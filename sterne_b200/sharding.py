@@ -23,9 +23,10 @@ class ShardedLikelihood(object):
     """Evaluates a global batch across the ranks of a torch.distributed process group.
 
     `likelihood` is a sterne_b200.Gaussianlikelihood built on this rank's GPU (or, in
-    CPU tests, any object with log_likelihood_batch(theta, lanes=...) -> (n,)).
-    The number of lanes per sample is chosen from the GLOBAL batch size, so a sample's
-    log-L has the same bits whatever the number of GPUs.
+    CPU tests, any object with log_likelihood_batch(theta, plan=...) -> (n,)).
+    The execution plan (lanes per sample, CTAs per tile; it fixes the summation order) is
+    chosen from the GLOBAL batch size, so a sample's log-L has the same bits whatever the
+    number of GPUs.
     """
 
     def __init__(self, likelihood, group=None):
@@ -36,17 +37,17 @@ class ShardedLikelihood(object):
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
 
-    def global_lanes(self, n_global):
+    def global_plan(self, n_global):
         ctx = getattr(self.like, '_context', None)
         if ctx is None:
             return 0
-        return ctx(None).auto_lanes(int(n_global))
+        return ctx(None).auto_plan(int(n_global))
 
     def local_slice(self, n_global):
         return shard_bounds(n_global, self.world, self.rank)
 
     def evaluate_local(self, theta_local, n_global, **kw):
-        return self.like.log_likelihood_batch(theta_local, lanes=self.global_lanes(n_global), **kw)
+        return self.like.log_likelihood_batch(theta_local, plan=self.global_plan(n_global), **kw)
 
     def all_gather(self, local_out, n_global):
         """(n_global,) log-L on every rank from the per-rank slices (one collective)."""

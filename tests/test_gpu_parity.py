@@ -6,6 +6,7 @@ import pytest
 
 import sterne_b200 as sb
 from sterne_b200 import synthetic, _lib
+from sterne_b200._lib import make_plan
 from oracle import sterne_oracle as O
 from conftest import rel_err, logl_err, logl_scale
 
@@ -113,9 +114,9 @@ def test_config5_shape_matches_oracle(variant):
     want = _oracle_batch(case, theta)
     scale = logl_scale(case.LoD_VLBI)
     like = case.likelihood()
-    for lanes in (0, 1, 4, 32):
-        got = like.log_likelihood_batch(theta, lanes=lanes)
-        assert logl_err(got, want, scale).max() < LOGL_RTOL, (variant, lanes, logl_err(got, want, scale).max())
+    for plan in (0, make_plan(1), make_plan(4), make_plan(32), make_plan(1, 8), make_plan(1, 64), make_plan(2, 5)):
+        got = like.log_likelihood_batch(theta, plan=plan)
+        assert logl_err(got, want, scale).max() < LOGL_RTOL, (variant, plan, logl_err(got, want, scale).max())
     got = like.log_likelihood_batch(theta, mode='strict')
     assert logl_err(got, want, scale).max() < LOGL_RTOL
     like.close()
@@ -132,18 +133,21 @@ def test_layouts_lanes_and_ragged_batches():
     for N in (1, 31, 33, 255, 257, 1000, 4097):
         theta = case.sample_theta(N, seed=N)
         want = _oracle_batch(case, theta)
-        base = like.log_likelihood_batch(theta, lanes=1)
+        base = like.log_likelihood_batch(theta, plan=make_plan(1))
         assert logl_err(base, want, scale).max() < LOGL_RTOL
         th = torch.from_numpy(theta).to(dev)
-        a = like.log_likelihood_batch(th, lanes=1)
-        s = like.log_likelihood_batch(th.t().contiguous(), layout='soa', lanes=1)
+        a = like.log_likelihood_batch(th, plan=make_plan(1))
+        s = like.log_likelihood_batch(th.t().contiguous(), layout='soa', plan=make_plan(1))
         assert torch.equal(a, s) and np.array_equal(a.cpu().numpy(), base)
         padded = torch.zeros((N, case.n_params + 3), dtype=torch.float64, device=dev)
         padded[:, :case.n_params] = th
-        assert torch.equal(like.log_likelihood_batch(padded[:, :case.n_params], lanes=1), a)
-        for lanes in (2, 4, 8, 16, 32):
-            got = like.log_likelihood_batch(th, lanes=lanes).cpu().numpy()
-            assert logl_err(got, want, scale).max() < LOGL_RTOL, (N, lanes)
+        assert torch.equal(like.log_likelihood_batch(padded[:, :case.n_params], plan=make_plan(1)), a)
+        for plan in (make_plan(2), make_plan(4), make_plan(8), make_plan(16), make_plan(32), make_plan(1, 2),
+                     make_plan(1, 5), make_plan(4, 3)):
+            got = like.log_likelihood_batch(th, plan=plan).cpu().numpy()
+            assert logl_err(got, want, scale).max() < LOGL_RTOL, (N, plan)
+            host = like.log_likelihood_batch(theta, plan=plan)          # host path: same bits as device path
+            assert np.array_equal(host, got), (N, plan)
     like.close()
 
 
@@ -195,7 +199,9 @@ def test_errors_are_loud():
     with pytest.raises(ValueError):
         like.log_likelihood_batch(np.zeros((4, case.n_params + 1)))
     with pytest.raises(_lib.StnError):
-        like.log_likelihood_batch(np.zeros((4, case.n_params)), lanes=3)
+        like.log_likelihood_batch(np.zeros((4, case.n_params)), plan=3)
+    with pytest.raises(_lib.StnError):
+        like.log_likelihood_batch(np.zeros((4, case.n_params)), plan=make_plan(1, 1000))
     assert like.log_likelihood_batch(np.zeros((0, case.n_params))).shape == (0,)
     like.close()
 
@@ -249,13 +255,14 @@ def test_sharded_slices_are_bit_identical():
     dev = torch.device('cuda', 0)
     N = 100003
     theta = synthetic.device_theta(case, N, seed=77, device=dev)
-    lanes = like._context(None).auto_lanes(N)
-    full = like.log_likelihood_batch(theta, lanes=lanes)
+    plan = like._context(None).auto_plan(N)
+    assert plan != make_plan(1)                       # a mid-size batch really is split over CTAs
+    full = like.log_likelihood_batch(theta, plan=plan)
     for world in (2, 4, 8):
         parts = []
         for r in range(world):
             lo, hi = shard_bounds(N, world, r)
-            parts.append(like.log_likelihood_batch(theta[lo:hi], lanes=lanes))
+            parts.append(like.log_likelihood_batch(theta[lo:hi], plan=plan))
         assert torch.equal(torch.cat(parts), full), world
     like.close()
 
@@ -305,10 +312,12 @@ def test_edge_shapes_match_oracle(epoch_counts, binaries, a1dot):
     scale = max(logl_scale(case.LoD_VLBI), 1.0)
     for mode in ('fast', 'strict'):
         like = case.likelihood(mode=mode)
-        for lanes in ((0, 1, 8, 32) if mode == 'fast' else (0,)):
-            got = like.log_likelihood_batch(theta, lanes=lanes)
+        nchunks = sum(max(1, -(-e // 128)) for e in epoch_counts)
+        plans = (0, make_plan(1), make_plan(8), make_plan(32), make_plan(1, nchunks), make_plan(2, min(2, nchunks)))
+        for plan in (plans if mode == 'fast' else (0,)):
+            got = like.log_likelihood_batch(theta, plan=plan)
             err = logl_err(got, want, scale)
-            assert err.max() < LOGL_RTOL, (epoch_counts, mode, lanes, err.max())
+            assert err.max() < LOGL_RTOL, (epoch_counts, mode, plan, err.max())
         like.close()
 
 
@@ -326,3 +335,22 @@ def test_extreme_variance_tables_take_the_safe_path():
     assert np.isfinite(want).all()
     assert (np.abs(got - want) / np.abs(want)).max() < 1e-9      # chi^2 ~ 1e90 dominates: pure relative check
     like.close()
+
+
+def test_chi_square_and_reduced_chi_square():
+    """stn_chisq against the oracle's residuals; calculate_reduced_chi_square as simulate.py:290-301."""
+    for case in (synthetic.config4(), synthetic.config5('C')):
+        theta = case.sample_theta(200, seed=31, scale=0.3)
+        names, idx = O.column_table(case.shares)
+        want = np.zeros(len(theta))
+        for i, v in enumerate(case.LoD_VLBI):
+            model, _ = O.batch_model(case.refepoch, v, case.earth_xyz[i], case.LoD_timing[i], idx[i], theta)
+            want += np.sum(((v['radecs'][None, :] - model) / O.batch_errs(v, idx[i], theta)) ** 2, axis=1)
+        for mode in ('fast', 'strict'):
+            like = case.likelihood(mode=mode)
+            got = like.chi_square_batch(theta)
+            assert (np.abs(got - want) / want).max() < 1e-9, (case.name, mode)     # chi^2 alone: ~1e-10 from model rounding flips
+            chi, rchi = like.calculate_reduced_chi_square(dict(zip(case.names, theta[0])))
+            dof = 2 * case.evals_per_sample - case.n_params
+            assert abs(chi - want[0]) / want[0] < 1e-9 and abs(rchi - want[0] / dof) / (want[0] / dof) < 1e-9
+            like.close()

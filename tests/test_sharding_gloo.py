@@ -1,4 +1,4 @@
-"""world_size-2 gloo test (CPU) of the multi-GPU host logic: slice bounds, the lanes
+"""world_size-2 gloo test (CPU) of the multi-GPU host logic: slice bounds, the plan
 choice from the GLOBAL batch, and the all_gather of per-rank log-L slices.  The
 per-slice evaluator is the oracle here (no GPU in this container); on a GPU box the
 same ShardedLikelihood wraps sterne_b200.Gaussianlikelihood."""
@@ -29,11 +29,11 @@ class _OracleLike(object):
 
     def __init__(self, case):
         self.case = case
-        self.seen_lanes = []
+        self.seen_plans = []
 
-    def log_likelihood_batch(self, theta, lanes=0, **kw):
+    def log_likelihood_batch(self, theta, plan=0, **kw):
         from oracle import sterne_oracle as O
-        self.seen_lanes.append(lanes)
+        self.seen_plans.append(plan)
         c = self.case
         return O.batch_log_likelihood(c.refepoch, c.LoD_timing, c.LoD_VLBI, c.shares, c.earth_xyz, np.asarray(theta))
 

@@ -10,7 +10,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--log2n', type=int, default=22)
 ap.add_argument('--steps', type=int, default=5)
 ap.add_argument('--variants', default='ABC')
-ap.add_argument('--lanes', type=int, default=0)
+ap.add_argument('--plan', type=int, default=0)
 ap.add_argument('--check', action='store_true')
 a = ap.parse_args()
 dev = torch.device('cuda', 0)
@@ -23,12 +23,12 @@ for v in a.variants:
     th = synthetic.device_theta(case, N, 1234, dev)
     out = torch.empty(N, dtype=torch.float64, device=dev)
     for _ in range(3):
-        like.log_likelihood_batch(th, out=out, lanes=a.lanes)
+        like.log_likelihood_batch(th, out=out, plan=a.plan)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
-        like.log_likelihood_batch(th, out=out, lanes=a.lanes)
+        like.log_likelihood_batch(th, out=out, plan=a.plan)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
     ev = N * case.evals_per_sample / (ms * 1e-3)
