@@ -49,6 +49,13 @@
 #ifndef STN_RBIG_EFAC
 #define STN_RBIG_EFAC 3
 #endif
+// CTA shape of the R = 3 kernel: threads per CTA and CTAs per SM it is compiled for
+#ifndef STN_THREADS_R3
+#define STN_THREADS_R3 256
+#endif
+#ifndef STN_MINBLOCKS_R3
+#define STN_MINBLOCKS_R3 1
+#endif
 #ifndef STN_CHUNK
 #define STN_CHUNK 128
 #endif
@@ -429,8 +436,11 @@ __device__ double prior_terms(const ProbDev& P, const double* __restrict__ theta
 // ---------------------------------------------------------------------------------
 // K1: fused FAST log-likelihood
 // ---------------------------------------------------------------------------------
+__host__ __device__ constexpr int threads_for(int R) { return R > 2 ? STN_THREADS_R3 : kThreads; }
+__host__ __device__ constexpr int minblocks_for(int R) { return R > 2 ? STN_MINBLOCKS_R3 : 2; }
+
 template <int R, int L>
-__global__ void __launch_bounds__(kThreads, (R > 2 ? 1 : 2))
+__global__ void __launch_bounds__(threads_for(R), minblocks_for(R))
 stn_loglike_fast_kernel(const ProbDev P, const double* __restrict__ theta, const int64_t N,
                         const int64_t ld, const int layout, double* __restrict__ out,
                         double* __restrict__ partial) {
@@ -440,7 +450,7 @@ stn_loglike_fast_kernel(const ProbDev P, const double* __restrict__ theta, const
     const int tid = threadIdx.x;
     const int sub = tid % L;
     const int grp = tid / L;
-    constexpr int G = kThreads / L;                     // sample groups per CTA
+    constexpr int G = threads_for(R) / L;               // sample groups per CTA
     const int64_t tile_base = (int64_t)blockIdx.x * (G * R);
 
     int64_t nidx[R];
@@ -813,8 +823,9 @@ int big_R(const StnCtx* ctx) { return ctx->efac_heavy ? STN_RBIG_EFAC : STN_RBIG
 int choose_R(const StnCtx* ctx, int64_t n, int lanes, int splits) {
     if (lanes != 1) return 1;
     const int R = big_R(ctx);
-    const int64_t slots = (int64_t)ctx->sm_count * (R > 2 ? 1 : 2);
-    const int64_t tiles = (n + (int64_t)kThreads * R - 1) / ((int64_t)kThreads * R);
+    const int64_t slots = (int64_t)ctx->sm_count * minblocks_for(R);
+    const int64_t tile = (int64_t)threads_for(R) * R;
+    const int64_t tiles = (n + tile - 1) / tile;
     return tiles * splits >= 2 * slots ? R : 1;
 }
 
@@ -822,8 +833,9 @@ int pick_plan(const StnCtx* ctx, int64_t n) {
     if (n <= 0) return make_plan(1, 1);
     const int T = ctx->prob.n_chunks;
     const int R = big_R(ctx);
-    const int64_t slots_big = (int64_t)ctx->sm_count * (R > 2 ? 1 : 2);
-    const int64_t tiles_big = (n + (int64_t)kThreads * R - 1) / ((int64_t)kThreads * R);
+    const int64_t slots_big = (int64_t)ctx->sm_count * minblocks_for(R);
+    const int64_t tile_big = (int64_t)threads_for(R) * R;
+    const int64_t tiles_big = (n + tile_big - 1) / tile_big;
     if (tiles_big >= 8 * slots_big) return make_plan(1, 1);          // >= 8 waves: no split needed
     // choose the number of splits that wastes the least of the last wave, given the tile count
     auto eff = [&](int64_t tiles, int64_t slots, int K) {
@@ -860,11 +872,11 @@ int pick_plan(const StnCtx* ctx, int64_t n) {
 template <int R, int L>
 int launch_fast(StnCtx* ctx, const ProbDev& prob, const double* theta, int64_t n, int64_t ld, int layout,
                 double* out, cudaStream_t st, int splits, double* partial) {
-    constexpr int per_cta = (kThreads / L) * R;
+    constexpr int per_cta = (threads_for(R) / L) * R;
     const int64_t grid = (n + per_cta - 1) / per_cta;
     if (grid > 0x7fffffffLL) return fail(STN_ERR_INVALID, "batch too large for one launch");
     dim3 g((unsigned)grid, (unsigned)splits, 1);
-    stn_loglike_fast_kernel<R, L><<<g, kThreads, 0, st>>>(prob, theta, n, ld, layout, out, partial);
+    stn_loglike_fast_kernel<R, L><<<g, threads_for(R), 0, st>>>(prob, theta, n, ld, layout, out, partial);
     STN_CUDA(cudaGetLastError());
     ctx->launches++;
     if (splits > 1) {
