@@ -12,6 +12,7 @@ from .shares import (get_parameters_from_shares, group_elements_by_same_values,
 from .readers import (readpmparin, create_list_of_dict_VLBI, read_parfile, create_list_of_dict_timing,
                       read_inits, dms2deg, dms_str2deg, decyear2mjd)
 from .ephemeris import (AnalyticEarthProvider, TableProvider, NovasDE421Provider, earth_vectors)
+from .jpleph import JPLEphemerisProvider
 from .problem import CompiledProblem, DeviceContext, fp64_peak
 from .likelihood import Gaussianlikelihood, positions, set_default_earth_provider
 

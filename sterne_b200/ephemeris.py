@@ -90,12 +90,26 @@ class AnalyticEarthProvider(object):
         return np.stack([x_ecl, ce * y_ecl - se * z_ecl, se * y_ecl + ce * z_ecl], axis=1)
 
 
+def tempo2_ephemeris_path():
+    tempo2_dir = os.getenv('TEMPO2')
+    if tempo2_dir is None:
+        return None
+    path = os.path.join(tempo2_dir, 'T2runtime/ephemeris/DE421.1950.2050')
+    return path if os.path.exists(path) else None
+
+
 def default_provider():
-    """novas + DE421 when importable and $TEMPO2 is set (the reference's path);
-    otherwise raises -- callers that want the analytic orbit must ask for it."""
+    """The reference's own source first (novas + $TEMPO2's DE421 file, positions.py:299-305);
+    if novas is not installed but the DE421 file is there, this package's native reader of
+    the same file (jpleph.JPLEphemerisProvider); otherwise raises -- callers that want the
+    analytic orbit must ask for it."""
     try:
         return NovasDE421Provider()
     except Exception as err:
+        path = tempo2_ephemeris_path()
+        if path is not None:
+            from .jpleph import JPLEphemerisProvider
+            return JPLEphemerisProvider(path)
         raise RuntimeError(
             'no Earth ephemeris available: novas/DE421 could not be opened (%s). Pass '
             'earth_provider=TableProvider(...) with vectors for your epochs, or '
