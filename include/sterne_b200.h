@@ -187,6 +187,22 @@ int stn_host_free(void* ptr);
  * Runs `reps` launches of `iters` FMA rounds, returns the best TFLOP/s and its time. */
 int stn_fp64_peak(int device, int iters, int reps, double* tflops, double* ms);
 
+/* Affine-invariant stretch move (Goodman & Weare 2010; what emcee runs for the reference,
+ * simulate.py:191-192) on device-resident walkers, so one ensemble half-step is three launches:
+ * propose -> stn_logpost -> accept.  x_dev: (n_walkers, n_params) row-major with leading
+ * dimension ld; the walkers of half `half` (0: rows [0, W/2), 1: rows [W/2, W)) are moved
+ * using partners drawn from the other half.  Random numbers: Philox4x32-10 keyed by `seed`,
+ * counter (walker, step, half) -- reproducible and independent of the launch geometry.
+ * y_dev: (W/2, n_params) proposals (leading dimension n_params), z_dev: (W/2) stretch factors. */
+int stn_stretch_propose(int device, const double* x_dev, int64_t n_walkers, int32_t n_params, int64_t ld,
+                        int half, double a, uint64_t seed, uint64_t step, double* y_dev, double* z_dev,
+                        void* stream);
+/* Accepts proposal k with probability min(1, z^(P-1) exp(lpy - lp)); updates x_dev / lp_dev in
+ * place and adds the number of acceptances to *n_accept_dev. */
+int stn_stretch_accept(int device, double* x_dev, double* lp_dev, int64_t n_walkers, int32_t n_params,
+                       int64_t ld, int half, uint64_t seed, uint64_t step, const double* y_dev,
+                       const double* z_dev, const double* lpy_dev, int64_t* n_accept_dev, void* stream);
+
 /* Timing helper for bench.py: runs `steps` back-to-back stn_loglike launches on an
  * internal stream bracketed by CUDA events on that stream; returns total ms. */
 int stn_loglike_timed(StnCtx* ctx, const double* theta_dev, int64_t n, int64_t ld,

@@ -46,7 +46,7 @@ def _worker(variant, rows, seed, start):
     print(json.dumps({'t0': t0, 't1': t1, 'evals': rows * case.evals_per_sample, 'checksum': float(out.sum())}))
 
 
-def time_vectorised(variant='C', rows_per_core=256, cores=None, seed=77, lead_s=12.0, timeout_s=600):
+def time_vectorised(variant='C', rows_per_core=256, cores=None, seed=77, lead_s=8.0, timeout_s=600):
     """(evals/s, wall seconds, cores): `cores` worker processes evaluating concurrently."""
     cores = cores or os.cpu_count() or 1
     start = time.time() + lead_s

@@ -76,6 +76,10 @@ SYMBOLS = [
     ('stn_host_alloc', _int, [ctypes.POINTER(_vp), _i64]),
     ('stn_host_free', _int, [_vp]),
     ('stn_fp64_peak', _int, [_int, _int, _int, c_double_p, c_double_p]),
+    ('stn_stretch_propose', _int, [_int, _vp, _i64, ctypes.c_int32, _i64, _int, ctypes.c_double, ctypes.c_uint64,
+                                   ctypes.c_uint64, _vp, _vp, _vp]),
+    ('stn_stretch_accept', _int, [_int, _vp, _vp, _i64, ctypes.c_int32, _i64, _int, ctypes.c_uint64, ctypes.c_uint64,
+                                  _vp, _vp, _vp, _vp, _vp]),
     ('stn_loglike_timed', _int, [_vp, _vp, _i64, _i64, _int, _int, _int, _vp, _int, c_double_p]),
 ]
 

@@ -749,6 +749,73 @@ __global__ void __launch_bounds__(256) stn_dfma_peak_kernel(double* sink, int it
 }
 
 // ---------------------------------------------------------------------------------
+// Stretch-move sampler steps (sampler adaptor)
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// uniform in (0, 1) from 53 random bits
+__device__ __forceinline__ double u01(uint32_t hi, uint32_t lo) {
+    const uint64_t k = (((uint64_t)hi << 32) | lo) >> 11;
+    return ((double)k + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+__global__ void __launch_bounds__(kThreads)
+stn_stretch_propose_kernel(const double* __restrict__ x, const int64_t W, const int P, const int64_t ld,
+                           const int half, const double a, const uint64_t seed, const uint64_t step,
+                           double* __restrict__ y, double* __restrict__ z_out) {
+    const int64_t H = W / 2;
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= H) return;
+    uint32_t r[4];
+    philox4x32_10((uint32_t)k, (uint32_t)(k >> 32), (uint32_t)step, (uint32_t)(step >> 32) ^ (half ? 0x80000000u : 0u),
+                  (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    const double u = u01(r[0], r[1]);
+    const double t = (a - 1.0) * u + 1.0;
+    const double z = t * t / a;                                       // g(z) ~ 1/sqrt(z) on [1/a, a]
+    const int64_t j = (int64_t)(u01(r[2], r[3]) * (double)H);         // partner in the complementary half
+    const double* xi = x + (half ? H + k : k) * ld;
+    const double* xj = x + (half ? j : H + j) * ld;
+    for (int p = 0; p < P; ++p) y[k * P + p] = xj[p] + z * (xi[p] - xj[p]);
+    z_out[k] = z;
+}
+
+__global__ void __launch_bounds__(kThreads)
+stn_stretch_accept_kernel(double* __restrict__ x, double* __restrict__ lp, const int64_t W, const int P,
+                          const int64_t ld, const int half, const uint64_t seed, const uint64_t step,
+                          const double* __restrict__ y, const double* __restrict__ z, const double* __restrict__ lpy,
+                          unsigned long long* __restrict__ n_accept) {
+    const int64_t H = W / 2;
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool acc = false;
+    if (k < H) {
+        uint32_t r[4];
+        philox4x32_10((uint32_t)k, (uint32_t)(k >> 32), (uint32_t)step,
+                      (uint32_t)(step >> 32) ^ (half ? 0xC0000000u : 0x40000000u), (uint32_t)seed,
+                      (uint32_t)(seed >> 32), r);
+        const int64_t i = half ? H + k : k;
+        const double lnq = (double)(P - 1) * log(z[k]) + lpy[k] - lp[i];
+        acc = (lpy[k] > -CUDART_INF) && (lpy[k] == lpy[k]) && (log(u01(r[0], r[1])) < lnq);
+        if (acc) {
+            for (int p = 0; p < P; ++p) x[i * ld + p] = y[k * P + p];
+            lp[i] = lpy[k];
+        }
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, acc);
+    if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(n_accept, (unsigned long long)__popc(ballot));
+}
+
+// ---------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------
 thread_local std::string g_err;
@@ -1284,6 +1351,37 @@ int stn_model(StnCtx* ctx, int source, const double* theta_dev, int64_t n, int64
         ctx->prob, source, theta_dev, n, ld, layout, mode, radec_dev, off_mas_dev);
     STN_CUDA(cudaGetLastError());
     ctx->launches++;
+    return STN_OK;
+}
+
+int stn_stretch_propose(int device, const double* x_dev, int64_t n_walkers, int32_t n_params, int64_t ld,
+                        int half, double a, uint64_t seed, uint64_t step, double* y_dev, double* z_dev,
+                        void* stream) {
+    if (!x_dev || !y_dev || !z_dev) return fail(STN_ERR_INVALID, "null buffer");
+    if (n_walkers < 2 || (n_walkers & 1) || n_params <= 0 || ld < n_params || !(a > 1.0) || (half != 0 && half != 1))
+        return fail(STN_ERR_INVALID, "stretch move needs an even number of walkers >= 2, ld >= P and a > 1");
+    STN_CUDA(cudaSetDevice(device));
+    const int64_t H = n_walkers / 2;
+    stn_stretch_propose_kernel<<<(unsigned)((H + kThreads - 1) / kThreads), kThreads, 0,
+                                 static_cast<cudaStream_t>(stream)>>>(x_dev, n_walkers, n_params, ld, half, a, seed,
+                                                                      step, y_dev, z_dev);
+    STN_CUDA(cudaGetLastError());
+    return STN_OK;
+}
+
+int stn_stretch_accept(int device, double* x_dev, double* lp_dev, int64_t n_walkers, int32_t n_params,
+                       int64_t ld, int half, uint64_t seed, uint64_t step, const double* y_dev,
+                       const double* z_dev, const double* lpy_dev, int64_t* n_accept_dev, void* stream) {
+    if (!x_dev || !lp_dev || !y_dev || !z_dev || !lpy_dev || !n_accept_dev) return fail(STN_ERR_INVALID, "null buffer");
+    if (n_walkers < 2 || (n_walkers & 1) || n_params <= 0 || ld < n_params || (half != 0 && half != 1))
+        return fail(STN_ERR_INVALID, "stretch move needs an even number of walkers >= 2 and ld >= P");
+    STN_CUDA(cudaSetDevice(device));
+    const int64_t H = n_walkers / 2;
+    stn_stretch_accept_kernel<<<(unsigned)((H + kThreads - 1) / kThreads), kThreads, 0,
+                                static_cast<cudaStream_t>(stream)>>>(
+        x_dev, lp_dev, n_walkers, n_params, ld, half, seed, step, y_dev, z_dev, lpy_dev,
+        reinterpret_cast<unsigned long long*>(n_accept_dev));
+    STN_CUDA(cudaGetLastError());
     return STN_OK;
 }
 

@@ -222,3 +222,81 @@ class EnsembleSampler(object):
     @property
     def acceptance_fraction(self):
         return float(self.naccepted) / max(self.nproposed, 1)
+
+
+class FusedEnsembleSampler(object):
+    """The same stretch move with every ensemble half-step as THREE library launches
+    (stn_stretch_propose -> stn_logpost -> stn_stretch_accept): walkers, proposals and
+    log-probabilities never leave the GPU and no torch arithmetic runs in the loop.
+
+        s = FusedEnsembleSampler(likelihood, prior, nwalkers, seed=1)
+        s.run(p0, nsteps, thin=10);  s.chain  # (nsteps // thin, nwalkers, ndim) CUDA tensor
+
+    Random numbers are counter-based (Philox keyed by `seed`): a run is reproducible and does
+    not depend on launch geometry.  Columns of p0 / chain follow prior.keys.
+    """
+
+    def __init__(self, likelihood, prior, nwalkers, a=2.0, seed=0, mode=None, plan=None):
+        import torch
+        from . import _lib
+        ndim = prior.ndim
+        if nwalkers % 2 or nwalkers < 2 * ndim:
+            raise ValueError('nwalkers must be even and at least 2*ndim')
+        self.torch = torch
+        self.lib = _lib.load()
+        self.check = _lib.check
+        self.like, self.prior = likelihood, prior
+        self.nwalkers, self.ndim, self.a, self.seed = nwalkers, ndim, float(a), int(seed)
+        self.device = torch.device('cuda', likelihood.device)
+        self.ctx = likelihood._context(prior.keys)
+        if self.ctx.prior is not prior:
+            self.ctx.set_prior(prior)
+        self.mode = likelihood.mode if mode is None else _lib.MODES[mode]
+        # the plan is fixed from the half-ensemble size once, so every step sums in the same order
+        self.plan = self.ctx.auto_plan(nwalkers // 2) if plan is None else int(plan)
+        self.step = 0
+        self.chain = None
+        self.lnprob = None
+        self.nproposed = 0
+        self._nacc = torch.zeros(1, dtype=torch.int64, device=self.device)
+
+    def run(self, p0, nsteps, thin=1, store=True):
+        torch = self.torch
+        W, P, H = self.nwalkers, self.ndim, self.nwalkers // 2
+        dev = self.device
+        x = torch.as_tensor(np.asarray(p0) if not _is_torch(p0) else p0).to(dev, torch.float64).contiguous().clone()
+        if tuple(x.shape) != (W, P):
+            raise ValueError('p0 must be (nwalkers, ndim)')
+        lp = torch.empty(W, dtype=torch.float64, device=dev)
+        y = torch.empty((H, P), dtype=torch.float64, device=dev)
+        z = torch.empty(H, dtype=torch.float64, device=dev)
+        lpy = torch.empty(H, dtype=torch.float64, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        from . import _lib
+        self.ctx.logpost_ptr(x.data_ptr(), W, P, _lib.LAYOUT_AOS, self.mode, self.ctx.auto_plan(W), lp.data_ptr(), stream)
+        if not bool(torch.isfinite(lp).all()):
+            raise ValueError('initial walkers must have finite log-probability')
+        nkeep = nsteps // thin if store else 0
+        if store:
+            self.chain = torch.empty((nkeep, W, P), dtype=torch.float64, device=dev)
+            self.lnprob = torch.empty((nkeep, W), dtype=torch.float64, device=dev)
+        d = self.like.device
+        for t in range(nsteps):
+            for half in (0, 1):
+                self.check(self.lib.stn_stretch_propose(d, x.data_ptr(), W, P, P, half, self.a, self.seed, self.step,
+                                                        y.data_ptr(), z.data_ptr(), stream))
+                self.ctx.logpost_ptr(y.data_ptr(), H, P, _lib.LAYOUT_AOS, self.mode, self.plan, lpy.data_ptr(), stream)
+                self.check(self.lib.stn_stretch_accept(d, x.data_ptr(), lp.data_ptr(), W, P, P, half, self.seed,
+                                                       self.step, y.data_ptr(), z.data_ptr(), lpy.data_ptr(),
+                                                       self._nacc.data_ptr(), stream))
+            self.step += 1
+            self.nproposed += W
+            if store and (t + 1) % thin == 0 and (t + 1) // thin <= nkeep:
+                self.chain[(t + 1) // thin - 1].copy_(x)
+                self.lnprob[(t + 1) // thin - 1].copy_(lp)
+        self.last = (x, lp)
+        return x, lp
+
+    @property
+    def acceptance_fraction(self):
+        return float(self._nacc.item()) / max(self.nproposed, 1)

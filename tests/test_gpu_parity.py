@@ -354,3 +354,25 @@ def test_chi_square_and_reduced_chi_square():
             dof = 2 * case.evals_per_sample - case.n_params
             assert abs(chi - want[0]) / want[0] < 1e-9 and abs(rchi - want[0] / dof) / (want[0] / dof) < 1e-9
             like.close()
+
+
+def test_host_entry_point_chunks_and_layouts():
+    """stn_loglike_host cuts big batches into 2^18-vector chunks on two streams; AoS, padded AoS
+    and SoA host buffers must all give the device path's bits."""
+    import torch
+    case = synthetic.config4()
+    like = case.likelihood()
+    N = (1 << 18) * 2 + 12345
+    dev = torch.device('cuda', 0)
+    th_dev = synthetic.device_theta(case, N, seed=3, device=dev)
+    plan = like._context(None).auto_plan(N)
+    want = like.log_likelihood_batch(th_dev, plan=plan).cpu().numpy()
+    th = th_dev.cpu().numpy()
+    assert np.array_equal(like.log_likelihood_batch(th, plan=plan), want)
+    assert np.array_equal(like.log_likelihood_batch(th), want)                     # plan chosen from the whole batch
+    padded = np.zeros((N, case.n_params + 5))
+    padded[:, :case.n_params] = th
+    assert np.array_equal(like.log_likelihood_batch(padded[:, :case.n_params], plan=plan), want)
+    soa = np.ascontiguousarray(th.T)
+    assert np.array_equal(like.log_likelihood_batch(soa, layout='soa', plan=plan), want)
+    like.close()

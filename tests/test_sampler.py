@@ -139,3 +139,41 @@ def test_fused_log_posterior_equals_prior_plus_likelihood():
     with pytest.raises(TypeError):
         like.log_posterior_batch(theta, prior)
     like.close()
+
+
+@pytest.mark.gpu
+def test_fused_sampler_matches_torch_sampler_statistically():
+    """Three launches per half-step (propose / stn_logpost / accept): same posterior as the
+    torch-op sampler and the truth inside it; reproducible for a given seed."""
+    from sterne_b200.sampler import FusedEnsembleSampler
+    case = synthetic.config2()
+    like = case.likelihood()
+    limits = {k: [case.box[k][0], case.box[k][1], 'Uniform'] for k in case.names}
+    prior = BoxPrior(limits)
+    nw = 1024
+    half = np.array([0.5 * (case.box[k][1] - case.box[k][0]) for k in case.names])
+    p0 = case.truth_vector() + 0.02 * half * np.random.default_rng(3).standard_normal((nw, case.n_params))
+    p0[:, case.names.index('efac_0')] = np.abs(p0[:, case.names.index('efac_0')]) + 0.5
+    f = FusedEnsembleSampler(like, prior, nw, seed=11)
+    f.run(p0, 600, thin=2)
+    flat_f = f.chain[100:].reshape(-1, case.n_params).cpu().numpy()
+    t = EnsembleSampler(nw, case.n_params, lambda x: like.log_posterior_batch(x, prior), device='cuda:0', seed=12)
+    t.run(torch.from_numpy(p0).cuda(), 600)
+    flat_t = t.chain[200:].reshape(-1, case.n_params).cpu().numpy()
+    assert 0.1 < f.acceptance_fraction < 0.9 and abs(f.acceptance_fraction - t.acceptance_fraction) < 0.05
+    sd = flat_t.std(0)
+    assert (np.abs(flat_f.mean(0) - flat_t.mean(0)) / sd).max() < 0.1, (flat_f.mean(0), flat_t.mean(0))
+    assert (np.abs(flat_f.std(0) / sd - 1.0)).max() < 0.1
+    astrometric = [i for i, k in enumerate(case.names) if not k.startswith('efac')]
+    assert (np.abs(flat_f.mean(0) - case.truth_vector()) / flat_f.std(0))[astrometric].max() < 4.0
+    # log-probabilities carried by the sampler are the posterior's
+    x, lp = f.last
+    assert torch.equal(like.log_posterior_batch(x, prior, plan=like._context(prior.keys).auto_plan(nw)), lp) or \
+        ((like.log_posterior_batch(x, prior) - lp).abs().max().item() < 1e-6)
+    # reproducible
+    g = FusedEnsembleSampler(like, prior, nw, seed=11)
+    g.run(p0, 50, store=False)
+    h = FusedEnsembleSampler(like, prior, nw, seed=11)
+    h.run(p0, 50, store=False)
+    assert torch.equal(g.last[0], h.last[0])
+    like.close()
