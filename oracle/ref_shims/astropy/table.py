@@ -17,3 +17,15 @@ class Table(object):
 
     def __len__(self):
         return len(self._c[self.colnames[0]])
+
+
+def _read_ascii(path):
+    """Table.read(path, format='ascii') for whitespace-separated numeric tables with a header line."""
+    with open(path) as f:
+        lines = [l for l in f.read().splitlines() if l.strip() and not l.startswith('#')]
+    names = lines[0].split()
+    data = np.array([[float(x) for x in l.split()] for l in lines[1:]], dtype=np.float64)
+    return Table([data[:, i] for i in range(len(names))], names)
+
+
+Table.read = staticmethod(lambda path, format='ascii': _read_ascii(path))

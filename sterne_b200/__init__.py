@@ -14,6 +14,7 @@ from .readers import (readpmparin, create_list_of_dict_VLBI, read_parfile, creat
 from .ephemeris import (AnalyticEarthProvider, TableProvider, NovasDE421Provider, earth_vectors)
 from .jpleph import JPLEphemerisProvider
 from .problem import CompiledProblem, DeviceContext, fp64_peak
+from . import summary
 from .likelihood import Gaussianlikelihood, positions, set_default_earth_provider
 
 __all__ = [n for n in dir() if not n.startswith('_')]

@@ -162,6 +162,47 @@ def run_case(case, tmp, n_theta=4):
     }
 
 
+def posterior_case(tmp):
+    """A synthetic posterior for config3 'dots' -> the reference's bayesian_estimates.dat text."""
+    from sterne import others as ref_others
+    case = synthetic.config3('dots')
+    files = synthetic.write_case_files(case, os.path.join(tmp, 'post'))
+    LoD_VLBI = quiet(ref_simulate.create_list_of_dict_VLBI, files['pmparins'], files['preliminaries'])
+    LoD_timing = quiet(ref_simulate.create_list_of_dict_timing, files['parfiles'])
+    rng = np.random.default_rng(42)
+    n = 1501
+    names = case.names
+    sig = {'ra': 3e-10, 'dec': 4e-10, 'mu_a': 0.05, 'mu_d': 0.06, 'px': 0.04, 'incl': 0.15, 'om_asc': 25.0}
+    cols = []
+    for k in names:
+        root = synthetic.parameter_name_to_pmparin_indice(k)[1]
+        mu = 350.0 if root == 'om_asc' else case.truth[k]          # straddles the 0/360 wrap
+        x = mu + sig[root] * rng.standard_normal(n)
+        cols.append(x % 360.0 if root == 'om_asc' else x)
+    cols[names.index('mu_d_0')] += 0.5 * (cols[names.index('mu_a_0')] - case.truth['mu_a_0'])   # a correlation
+    table = np.stack(cols + [rng.standard_normal(n), rng.standard_normal(n)], axis=1)
+    samplefile = os.path.join(tmp, 'post', 'posterior_samples.dat')
+    with open(samplefile, 'w') as f:
+        f.write(' '.join(names + ['log_likelihood', 'log_prior']) + '\n')
+        for row in table:
+            f.write(' '.join(repr(float(v)) for v in row) + '\n')
+    quiet(ref_simulate.make_a_summary_of_bayesian_inference, samplefile, case.refepoch, LoD_VLBI, LoD_timing)
+    text = open(samplefile.replace('posterior_samples', 'bayesian_estimates')).read()
+    est = []
+    for seed, m in ((1, 400), (2, 401), (3, 1000)):
+        x = np.random.default_rng(seed).standard_normal(m) * 3 + 1
+        ang = (np.random.default_rng(seed).standard_normal(m) * 30 + 355) % 360
+        est.append({'x': x.tolist(), 'ang': ang.tolist(), 'median': float(ref_others.sample2median(x)),
+                    'range1': [float(v) for v in ref_others.sample2median_range(x, 1)],
+                    'range2': [float(v) for v in ref_others.sample2median_range(x, 2)],
+                    'periodic': [float(v) for v in ref_others.periodic_sample2estimate(ang)]})
+    dms = [{'deg': d, 'dms': ref_others.deg2dms(float(d))} for d in (12.3456789, -0.5, 359.9999999, 0.0, -45.25)]
+    return {'case': 'config3_dots', 'posterior_samples': open(samplefile).read(), 'bayesian_estimates': text,
+            'estimators': est, 'deg2dms': dms,
+            'earth_xyz': [np.array([solsys.solarsystem(t + 2400000.5, 3, 0)[0] for t in d['epochs']]).tolist()
+                          for d in LoD_VLBI]}
+
+
 def main():
     out = {'generator': 'tests/golden/make_golden.py', 'reference': 'dingswin/sterne 1.0.2 (/root/reference)',
            'note': 'outputs of the unmodified reference run under oracle/ref_shims stand-ins', 'cases': [],
@@ -188,6 +229,11 @@ def main():
     for y in [57123.456, 10000.5, 2015.0, 2016.5, 2020.123456, 1999.999]:
         out['decyear2mjd'].append({'epoch': y, 'mjd': float(ref_simulate.decyear2mjd(y)),
                                    'pinned': bool(y > 10000)})   # decimal-year branch is the Time stand-in
+    with tempfile.TemporaryDirectory() as tmp:
+        post = posterior_case(tmp)
+    with open(os.path.join(HERE, 'golden_posterior_summary.json'), 'w') as f:
+        json.dump(post, f)
+    print('wrote golden_posterior_summary.json')
     path = os.path.join(HERE, 'golden_reference.json')
     with open(path, 'w') as f:
         json.dump(out, f)
