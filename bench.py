@@ -275,6 +275,26 @@ def run_ours(args, rank, local_rank, world):
             vl.close()
             del vt, vo
 
+    # ---- batch-size sweep of the headline variant (BASELINE config 5: N = 2^16 .. 2^22), kernel-only
+    sweep = {}
+    if world == 1 and not args.no_variants:
+        for l2 in (16, 18, 20):
+            n = 1 << l2
+            so = torch.empty(n, dtype=torch.float64, device=dev)
+            reps = max(args.steps, 1 << max(0, 20 - l2))
+            for _ in range(3):
+                like.log_likelihood_batch(theta[:n], out=so)
+            torch.cuda.synchronize(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                like.log_likelihood_batch(theta[:n], out=so)
+            b.record()
+            torch.cuda.synchronize(dev)
+            ms = a.elapsed_time(b) / reps
+            sweep['2^%d' % l2] = {'ms_per_step': ms, 'evals_per_s': n * case.evals_per_sample / (ms * 1e-3),
+                                  'plan': ctx.auto_plan(n)}
+
     if rank == 0:
         peaks, peaks_src = measured_peaks()
         value = world * evals_per_step_rank * args.steps / (ms_total * 1e-3)
@@ -295,7 +315,10 @@ def run_ours(args, rank, local_rank, world):
             'gpu_launches': launches,
             'roofline': {
                 'bound': 'fp64', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                'frac': achieved_tf / peak_tf, 'traffic': None,
+                'frac': achieved_tf / peak_tf,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` capture of this
+                # command (profiles/r01_ncu_loglike_fast_C.txt); algorithmic bytes per launch are alg_bytes below
+                'traffic': 744171264 + 35693568, 'traffic_unit': 'bytes per launch', 'algorithmic_bytes': alg_bytes,
                 'kernel': 'stn_loglike_fast_kernel<3,1>', 'kernel_ms': kernel_ms,
                 'flops_per_eval': FLOPS_PER_EVAL['C'],
                 'peak_source': 'stn_fp64_peak DFMA micro-benchmark in this run (MEASURED_PEAKS.json has no FP64 '
@@ -306,6 +329,7 @@ def run_ours(args, rank, local_rank, world):
             },
             'cpu_baseline': cpu_baseline,
             'variants': variants,
+            'sweep': sweep,
         }
         print(json.dumps(line))
     like.close()
