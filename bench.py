@@ -110,19 +110,15 @@ def run_reference(args, rank, world):
         return 0
     from oracle import cpu_bench                      # the one place bench.py executes oracle/
     cores = os.cpu_count() or 1
-    rows = args.cpu_rows
-    for _ in range(args.warmup and 1):
-        cpu_bench.time_vectorised('C', rows_per_core=16, cores=cores)
-    vals, walls = [], []
+    rows = cpu_rows(args, cpu_bench, cores, target_s=10.0)      # includes the warm-up call
+    walls = []
     for _ in range(args.steps):
-        v, w, c = cpu_bench.time_vectorised('C', rows_per_core=rows, cores=cores)
-        vals.append(v)
+        v, w, c = cpu_bench.time_c_oracle('C', rows=rows, threads=cores)
         walls.append(w)
-    total_evals = args.steps * cores * rows * 8 * 1024
-    value = total_evals / sum(walls)
-    sample = ('%d rows/core x %d cores x 8 sources x 1024 epochs per step (of the 2^%d-row workload), '
-              'numpy-vectorised restatement of simulate.py:362-384, one process per core'
-              % (rows, cores, LOG2_N))
+    value = args.steps * rows * 8 * 1024 / sum(walls)
+    sample = ('%d parameter vectors x 8 sources x 1024 epochs per step (of the 2^%d-vector workload); C restatement '
+              'of simulate.py:362-384 in the reference\'s operation order (oracle/c/sterne_oracle.c), OpenMP over %d '
+              'host threads' % (rows, LOG2_N, cores))
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * sum(walls) / args.steps,
@@ -136,6 +132,16 @@ def run_reference(args, rank, world):
     }
     print(json.dumps(line))
     return 0
+
+
+def cpu_rows(args, cpu_bench, cores, target_s):
+    """Size of the bounded CPU sample: --cpu-rows if given, else enough parameter vectors for about
+    `target_s` seconds on this host (calibrated with a short run that doubles as the warm-up)."""
+    if args.cpu_rows > 0:
+        return args.cpu_rows
+    v, _, _ = cpu_bench.time_c_oracle('C', rows=cores * 256, threads=cores)
+    rows = int(v * target_s / (8 * 1024))
+    return max(cores * 256, min(rows, 1 << LOG2_N))
 
 
 def workload_config(n_gpus):
@@ -161,12 +167,16 @@ def run_ours(args, rank, local_rank, world):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import cpu_bench                  # cpu_baseline leg: checker timed, never shipped
         cores = os.cpu_count() or 1
-        v, w, c = cpu_bench.time_vectorised('C', rows_per_core=args.cpu_rows, cores=cores)
+        args.cpu_rows = cpu_rows(args, cpu_bench, cores, target_s=15.0)
+        v, w, c = cpu_bench.time_c_oracle('C', rows=args.cpu_rows, threads=cores)
+        nv, nw, nc = cpu_bench.time_vectorised('C', rows_per_core=1024, cores=cores)
         sv, sw = cpu_bench.time_scalar('C', rows=2)
         cpu_baseline = {
             'value': v, 'unit': UNIT, 'cores': c, 'kind': 'port',
-            'sample': '%d rows/core x %d cores of the same 8-source x 1024-epoch problem (%.1f s); '
-                      'numpy-vectorised restatement, one process per core' % (args.cpu_rows, c, w),
+            'sample': '%d parameter vectors of the same 8-source x 1024-epoch problem (%.1f s wall on %d threads); '
+                      'C restatement in the reference\'s operation order, OpenMP' % (args.cpu_rows, w, c),
+            'numpy_vectorised_value': nv, 'numpy_vectorised_cores': nc,
+            'numpy_vectorised_sample': '1024 rows/core, one process per core (%.1f s)' % nw,
             'scalar_value': sv, 'scalar_cores': 1,
             'scalar_sample': '2 rows through the reference-shaped per-vector Python loop (%.1f s)' % sw}
 
@@ -344,7 +354,8 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--cpu-rows', type=int, default=4096, help='rows per core of the bounded CPU sample')
+    ap.add_argument('--cpu-rows', type=int, default=0,
+                    help='parameter vectors in the bounded CPU sample (0: calibrate to ~10-15 s of wall time)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-variants', action='store_true')
     args = ap.parse_args()

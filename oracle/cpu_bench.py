@@ -1,6 +1,8 @@
 """CPU timing of the oracle (TEST / BENCH INFRASTRUCTURE ONLY; see sterne_oracle.py header).
 
-Times the numpy restatement of the reference's likelihood on the host cores:
+Times the CPU restatements of the reference's likelihood on the host cores:
+  * `c_oracle`: the plain-C restatement (reference operation order), OpenMP over all cores --
+    the strongest CPU arm, used as THE cpu baseline;
   * `vectorised`: batch_log_likelihood over rows, one worker PROCESS per core, all
     started on a common wall-clock tick so they load the machine together;
   * `scalar`: the reference-shaped per-vector Python loop (Gaussianlikelihood.log_likelihood),
@@ -71,6 +73,22 @@ def time_vectorised(variant='C', rows_per_core=256, cores=None, seed=77, lead_s=
     t1 = max(r['t1'] for r in results)
     evals = sum(r['evals'] for r in results)
     return evals / (t1 - t0), t1 - t0, cores
+
+
+def time_c_oracle(variant='C', rows=1 << 15, threads=None, seed=79, repeats=1):
+    """(evals/s, wall seconds, threads) of the threaded C restatement (oracle/c/sterne_oracle.c):
+    the reference's operation order, one parameter vector per inner call, all host cores."""
+    from oracle import c_oracle
+    case = _case(variant)
+    threads = threads or os.cpu_count() or 1
+    co = c_oracle.from_case(case)
+    theta = case.sample_theta(rows, seed=seed, scale=0.3)
+    co.log_likelihood_batch(theta[:threads * 8], nthreads=threads)           # warm-up
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        co.log_likelihood_batch(theta, nthreads=threads)
+    wall = time.perf_counter() - t0
+    return repeats * rows * case.evals_per_sample / wall, wall, threads
 
 
 def time_scalar(variant='C', rows=1, seed=78):

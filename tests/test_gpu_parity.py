@@ -376,3 +376,17 @@ def test_host_entry_point_chunks_and_layouts():
     soa = np.ascontiguousarray(th.T)
     assert np.array_equal(like.log_likelihood_batch(soa, layout='soa', plan=plan), want)
     like.close()
+
+
+def test_large_batch_against_the_c_oracle():
+    """2^15 vectors of the full benchmark problem (2.7e8 evals) checked against the threaded C
+    restatement of the oracle -- a batch the numpy oracle is too slow for."""
+    from oracle import c_oracle
+    case = synthetic.config5('C')
+    theta = case.sample_theta(1 << 15, seed=41, scale=0.5)
+    want = c_oracle.from_case(case).log_likelihood_batch(theta)
+    like = case.likelihood()
+    got = like.log_likelihood_batch(theta)
+    err = logl_err(got, want, logl_scale(case.LoD_VLBI))
+    assert err.max() < LOGL_RTOL, (err.max(), int((err > LOGL_RTOL).sum()))
+    like.close()
