@@ -139,7 +139,8 @@ def cpu_rows(args, cpu_bench, cores, target_s):
     `target_s` seconds on this host (calibrated with a short run that doubles as the warm-up)."""
     if args.cpu_rows > 0:
         return args.cpu_rows
-    v, _, _ = cpu_bench.time_c_oracle('C', rows=cores * 256, threads=cores)
+    cpu_bench.time_c_oracle('C', rows=cores * 64, threads=cores)
+    v, _, _ = cpu_bench.time_c_oracle('C', rows=cores * 2048, threads=cores)
     rows = int(v * target_s / (8 * 1024))
     return max(cores * 256, min(rows, 1 << LOG2_N))
 
