@@ -390,3 +390,33 @@ def test_large_batch_against_the_c_oracle():
     err = logl_err(got, want, logl_scale(case.LoD_VLBI))
     assert err.max() < LOGL_RTOL, (err.max(), int((err > LOGL_RTOL).sum()))
     like.close()
+
+
+def test_tooling_entry_points():
+    """stn_loglike_timed, stn_fp64_peak, stn_launch_count, stn_auto_plan, stn_host_alloc/free."""
+    import ctypes
+    import torch
+    import sterne_b200 as sb
+    case = synthetic.config4()
+    like = case.likelihood()
+    ctx = like._context(None)
+    th = torch.from_numpy(case.sample_theta(4096, seed=1)).cuda()
+    out = torch.empty(4096, dtype=torch.float64, device='cuda')
+    before = ctx.launch_count()
+    ms = ctx.loglike_timed(th.data_ptr(), 4096, case.n_params, _lib.LAYOUT_AOS, _lib.MODE_FAST, make_plan(1),
+                           out.data_ptr(), 5)
+    assert ms > 0 and ctx.launch_count() - before == 5
+    assert torch.equal(out, like.log_likelihood_batch(th, plan=make_plan(1)))
+    lanes, splits = _lib.plan_parts(ctx.auto_plan(100))
+    assert lanes in (1, 2, 4, 8, 16, 32) and splits >= 1
+    assert _lib.plan_parts(ctx.auto_plan(1 << 22)) == (1, 1)
+    tf, _ = sb.fp64_peak(0, iters=1 << 12, reps=2)
+    assert 20.0 < tf < 45.0                        # B200: 37.2 TFLOP/s nominal
+    p = ctypes.c_void_p()
+    lib = _lib.load()
+    _lib.check(lib.stn_host_alloc(ctypes.byref(p), 1 << 20))
+    host = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_double)), shape=(64, case.n_params))
+    host[:] = case.sample_theta(64, seed=2)
+    assert np.array_equal(like.log_likelihood_batch(host), like.log_likelihood_batch(host.copy()))
+    _lib.check(lib.stn_host_free(p))
+    like.close()
