@@ -86,6 +86,7 @@ class Gaussianlikelihood(_LikelihoodBase):
         self._provider = _resolve_provider(earth_provider) if (needs_px and earth_xyz is None) else earth_provider
         self._earth_xyz = earth_xyz
         self._contexts = {}
+        self._one = None
         ctx = self._context(None)
         super().__init__(dict.fromkeys(ctx.problem.default_names))
 
@@ -118,11 +119,23 @@ class Gaussianlikelihood(_LikelihoodBase):
         return self._context(None).problem.evals_per_sample
 
     # ------------------------------------------------------------ reference API
-    def log_likelihood(self):
-        """simulate.py:362: one parameter vector taken from self.parameters."""
-        names = self.parameter_names
-        theta = np.array([[float(self.parameters[k]) for k in names]], dtype=np.float64)
-        return float(self.log_likelihood_batch(theta)[0])
+    def log_likelihood(self, parameters=None):
+        """simulate.py:362: one parameter vector taken from self.parameters (or, for bilby
+        versions that pass it, from the `parameters` argument).  A batch of one."""
+        one = self._one
+        if one is None:
+            ctx = self._context(None)
+            names = tuple(ctx.problem.default_names)
+            theta = np.empty((1, len(names)), dtype=np.float64)
+            out = np.empty(1, dtype=np.float64)
+            one = self._one = (ctx, names, theta, out, theta.ctypes.data, out.ctypes.data)
+        ctx, names, theta, out, tp, op = one
+        src = self.parameters if parameters is None else parameters
+        row = theta[0]
+        for i, k in enumerate(names):
+            row[i] = src[k]
+        ctx.loglike_host_ptr(tp, 1, len(names), _lib.LAYOUT_AOS, self.mode, self.plan, op)
+        return float(out[0])
 
     # ------------------------------------------------------------- batched API
     def log_likelihood_batch(self, theta, keys=None, out=None, layout='aos', mode=None, plan=None):
@@ -254,6 +267,7 @@ class Gaussianlikelihood(_LikelihoodBase):
                 seen.add(id(ctx))
                 ctx.close()
         self._contexts = {}
+        self._one = None
 
 
 # ------------------------------------------------------------------------------------

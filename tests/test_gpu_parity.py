@@ -420,3 +420,25 @@ def test_tooling_entry_points():
     assert np.array_equal(like.log_likelihood_batch(host), like.log_likelihood_batch(host.copy()))
     _lib.check(lib.stn_host_free(p))
     like.close()
+
+
+def test_very_large_batch_indexing():
+    """2^25 + 3 vectors (5 GB of parameters): 64-bit indexing everywhere; spot-check against the oracle."""
+    import torch
+    case = synthetic.config5('A', n_sources=2, n_epochs=64)
+    dev = torch.device('cuda', 0)
+    N = (1 << 25) + 3
+    theta = synthetic.device_theta(case, N, seed=8, device=dev)
+    like = case.likelihood()
+    out = like.log_likelihood_batch(theta)
+    assert bool(torch.isfinite(out).all())
+    pick = torch.tensor([0, 1, 12345, (1 << 24) + 7, (1 << 25) - 1, N - 2, N - 1], device=dev)
+    want = _oracle_batch(case, theta[pick].cpu().numpy())
+    err = logl_err(out[pick].cpu().numpy(), want, logl_scale(case.LoD_VLBI))
+    assert err.max() < LOGL_RTOL
+    soa = theta[-(1 << 20):].t().contiguous()                      # SoA view of the tail
+    assert torch.equal(like.log_likelihood_batch(soa, layout='soa', plan=make_plan(1)),
+                       like.log_likelihood_batch(theta[-(1 << 20):], plan=make_plan(1)))
+    like.close()
+    del theta, out
+    torch.cuda.empty_cache()
