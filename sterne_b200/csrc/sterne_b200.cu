@@ -851,6 +851,9 @@ struct StnCtx {
     bool has_prior = false;
     std::vector<void*> prior_allocs;
     bool efac_heavy = false;            // at least half of the epochs belong to EFAC sources
+    // zero-copy staging for small host batches (pinned, mapped: the kernel reads / writes it directly)
+    double* small_in = nullptr;
+    double* small_out = nullptr;
     double* scratch[3] = {nullptr, nullptr, nullptr};   // split partial sums: [0] device API, [1],[2] host streams
     int64_t scratch_elems[3] = {0, 0, 0};
     int64_t launches = 0;
@@ -943,6 +946,7 @@ int launch_fast(StnCtx* ctx, const ProbDev& prob, const double* theta, int64_t n
     const int64_t grid = (n + per_cta - 1) / per_cta;
     if (grid > 0x7fffffffLL) return fail(STN_ERR_INVALID, "batch too large for one launch");
     dim3 g((unsigned)grid, (unsigned)splits, 1);
+    (void)cudaGetLastError();      // other CUDA users of this process (torch) may have left a stale error
     stn_loglike_fast_kernel<R, L><<<g, threads_for(R), 0, st>>>(prob, theta, n, ld, layout, out, partial);
     STN_CUDA(cudaGetLastError());
     ctx->launches++;
@@ -964,6 +968,7 @@ int launch_loglike(StnCtx* ctx, const double* theta, int64_t n, int64_t ld, int 
     prob.out_chisq = what == 2 ? 1 : 0;
     if (mode == STN_MODE_STRICT) {
         const int64_t grid = (n + kThreads - 1) / kThreads;
+        (void)cudaGetLastError();
         stn_loglike_strict_kernel<<<(unsigned)grid, kThreads, 0, st>>>(prob, theta, n, ld, layout, out);
         STN_CUDA(cudaGetLastError());
         ctx->launches++;
@@ -1151,6 +1156,8 @@ int stn_destroy(StnCtx* ctx) {
     for (void* p : ctx->prior_allocs) cudaFree(p);
     for (int i = 0; i < 3; ++i)
         if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    if (ctx->small_in) cudaFreeHost(ctx->small_in);
+    if (ctx->small_out) cudaFreeHost(ctx->small_out);
     for (int i = 0; i < 2; ++i) {
         if (ctx->stage_theta[i]) cudaFree(ctx->stage_theta[i]);
         if (ctx->stage_out[i]) cudaFree(ctx->stage_out[i]);
@@ -1210,6 +1217,8 @@ int stn_set_prior(StnCtx* ctx, const StnPrior* pr) {
     for (void* p : ctx->prior_allocs) cudaFree(p);
     for (int i = 0; i < 3; ++i)
         if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    if (ctx->small_in) cudaFreeHost(ctx->small_in);
+    if (ctx->small_out) cudaFreeHost(ctx->small_out);
     ctx->prior_allocs.clear();
     ctx->has_prior = false;
     ProbDev P = ctx->prob;
@@ -1285,6 +1294,24 @@ int stn_loglike_host(StnCtx* ctx, const double* theta_host, int64_t n, int64_t l
     if (n == 0) return STN_OK;
     STN_CUDA(cudaSetDevice(ctx->device));
     const int P = ctx->prob.n_params;
+    for (int i = 0; i < 2; ++i)
+        if (!ctx->streams[i]) STN_CUDA(cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking));
+    // Small batches (a sampler evaluating one point, or a few walkers) are latency-bound: skip both
+    // cudaMemcpy calls by letting the kernel read the parameters from, and write log L to, pinned
+    // mapped host memory.  One launch + one stream synchronise.
+    constexpr int64_t kSmallBytes = 64 * 1024, kSmallRows = 2048;
+    if (layout == STN_LAYOUT_AOS && n <= kSmallRows && n * P * (int64_t)sizeof(double) <= kSmallBytes) {
+        if (!ctx->small_in) {
+            STN_CUDA(cudaHostAlloc((void**)&ctx->small_in, kSmallBytes, cudaHostAllocMapped));
+            STN_CUDA(cudaHostAlloc((void**)&ctx->small_out, kSmallRows * sizeof(double), cudaHostAllocMapped));
+        }
+        for (int64_t i = 0; i < n; ++i) std::memcpy(ctx->small_in + i * P, theta_host + i * ld, (size_t)P * sizeof(double));
+        rc = launch_loglike(ctx, ctx->small_in, n, P, layout, mode, plan, ctx->small_out, ctx->streams[0], 0, 1);
+        if (rc) return rc;
+        STN_CUDA(cudaStreamSynchronize(ctx->streams[0]));
+        std::memcpy(out_host, ctx->small_out, (size_t)n * sizeof(double));
+        return STN_OK;
+    }
     // chunk so that copies of chunk i+1 overlap the kernel of chunk i
     int64_t rows = n;
     const int64_t max_rows = (int64_t)1 << 18;
@@ -1302,8 +1329,6 @@ int stn_loglike_host(StnCtx* ctx, const double* theta_host, int64_t n, int64_t l
         }
         ctx->stage_rows = rows;
     }
-    for (int i = 0; i < 2; ++i)
-        if (!ctx->streams[i]) STN_CUDA(cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking));
     if (mode == STN_MODE_FAST && plan == 0) plan = pick_plan(ctx, n);    // from the whole batch
     int k = 0;
     for (int64_t lo = 0; lo < n; lo += rows, ++k) {
@@ -1347,6 +1372,7 @@ int stn_model(StnCtx* ctx, int source, const double* theta_dev, int64_t n, int64
     STN_CUDA(cudaSetDevice(ctx->device));
     const int64_t grid = (total + kThreads - 1) / kThreads;
     if (grid > 0x7fffffffLL) return fail(STN_ERR_INVALID, "batch too large for one launch");
+    (void)cudaGetLastError();
     stn_model_kernel<<<(unsigned)grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         ctx->prob, source, theta_dev, n, ld, layout, mode, radec_dev, off_mas_dev);
     STN_CUDA(cudaGetLastError());
@@ -1362,6 +1388,7 @@ int stn_stretch_propose(int device, const double* x_dev, int64_t n_walkers, int3
         return fail(STN_ERR_INVALID, "stretch move needs an even number of walkers >= 2, ld >= P and a > 1");
     STN_CUDA(cudaSetDevice(device));
     const int64_t H = n_walkers / 2;
+    (void)cudaGetLastError();
     stn_stretch_propose_kernel<<<(unsigned)((H + kThreads - 1) / kThreads), kThreads, 0,
                                  static_cast<cudaStream_t>(stream)>>>(x_dev, n_walkers, n_params, ld, half, a, seed,
                                                                       step, y_dev, z_dev);
@@ -1377,6 +1404,7 @@ int stn_stretch_accept(int device, double* x_dev, double* lp_dev, int64_t n_walk
         return fail(STN_ERR_INVALID, "stretch move needs an even number of walkers >= 2 and ld >= P");
     STN_CUDA(cudaSetDevice(device));
     const int64_t H = n_walkers / 2;
+    (void)cudaGetLastError();
     stn_stretch_accept_kernel<<<(unsigned)((H + kThreads - 1) / kThreads), kThreads, 0,
                                 static_cast<cudaStream_t>(stream)>>>(
         x_dev, lp_dev, n_walkers, n_params, ld, half, seed, step, y_dev, z_dev, lpy_dev,
