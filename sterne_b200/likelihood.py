@@ -291,7 +291,8 @@ def positions(refepoch, epochs, dict_timing, parameter_filter_index, dict_parame
     vals = [float(FP[k]) for k in keys]          # dec, efac, efad, incl, mu_a, mu_d, om_asc, px, ra
     present = [v != SENTINEL for v in vals]
     tkey = tuple(sorted((k, v) for k, v in dict_timing.items())) if dict_timing != {} else ()
-    key = (float(refepoch), epochs.tobytes(), tkey, tuple(present), int(device), id(earth_provider))
+    # the provider object itself is part of the key (kept alive by the cache), not its id()
+    key = (float(refepoch), epochs.tobytes(), tkey, tuple(present), int(device), earth_provider)
     like = _positions_cache.get(key)
     if like is None:
         E = epochs.shape[0]

@@ -1,6 +1,5 @@
 """CPU-side tests of the product's host logic (no GPU): readers, parameter naming and
 routing, orbit precompute, problem compiler, and the C-ABI library's exported symbols."""
-import ctypes
 import os
 import re
 

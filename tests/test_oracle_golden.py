@@ -1,7 +1,6 @@
 """Pins the CPU oracle (oracle/sterne_oracle.py) against outputs of the UNMODIFIED
 reference recorded in tests/golden/golden_reference.json (see make_golden.py)."""
 import numpy as np
-import pytest
 
 from oracle import sterne_oracle as O
 from conftest import rel_err
