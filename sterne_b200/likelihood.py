@@ -164,6 +164,9 @@ class Gaussianlikelihood(_LikelihoodBase):
             n, ld = self._shape(theta.shape, theta.stride(0), lay, P)
             if out is None:
                 out = torch.empty(n, dtype=torch.float64, device=theta.device)
+            elif (not _is_torch_tensor(out) or out.dtype != torch.float64 or out.device != theta.device
+                  or out.numel() != n or not out.is_contiguous()):
+                raise TypeError('out must be a contiguous float64 tensor of %d elements on %s' % (n, theta.device))
             stream = torch.cuda.current_stream(theta.device).cuda_stream
             ctx.loglike_ptr(theta.data_ptr(), n, ld, lay, mode, plan, out.data_ptr(), stream)
             return out
@@ -175,6 +178,9 @@ class Gaussianlikelihood(_LikelihoodBase):
         n, ld = self._shape(theta.shape, theta.strides[0] // 8, lay, P)
         if out is None:
             out = np.empty(n, dtype=np.float64)
+        elif (not isinstance(out, np.ndarray) or out.dtype != np.float64 or out.shape != (n,)
+              or not out.flags['C_CONTIGUOUS'] or not out.flags['WRITEABLE']):
+            raise TypeError('out must be a writable C-contiguous float64 array of shape (%d,)' % n)
         ctx.loglike_host_ptr(theta.ctypes.data, n, ld, lay, mode, plan, out.ctypes.data)
         return out
 
@@ -198,6 +204,9 @@ class Gaussianlikelihood(_LikelihoodBase):
         n, ld = self._shape(theta.shape, theta.stride(0), _lib.LAYOUT_AOS, ctx.problem.n_params)
         if out is None:
             out = torch.empty(n, dtype=torch.float64, device=theta.device)
+        elif (not _is_torch_tensor(out) or out.dtype != torch.float64 or out.device != theta.device
+              or out.numel() != n or not out.is_contiguous()):
+            raise TypeError('out must be a contiguous float64 tensor of %d elements on %s' % (n, theta.device))
         stream = torch.cuda.current_stream(theta.device).cuda_stream
         ctx.logpost_ptr(theta.data_ptr(), n, ld, _lib.LAYOUT_AOS, mode, plan, out.data_ptr(), stream)
         return out

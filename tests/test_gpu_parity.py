@@ -203,6 +203,10 @@ def test_errors_are_loud():
     with pytest.raises(_lib.StnError):
         like.log_likelihood_batch(np.zeros((4, case.n_params)), plan=make_plan(1, 1000))
     assert like.log_likelihood_batch(np.zeros((0, case.n_params))).shape == (0,)
+    with pytest.raises(TypeError):
+        like.log_likelihood_batch(np.zeros((4, case.n_params)), out=np.zeros(3))
+    with pytest.raises(TypeError):
+        like.log_likelihood_batch(np.zeros((4, case.n_params)), out=np.zeros(4, dtype=np.float32))
     like.close()
 
 
