@@ -15,7 +15,7 @@ from .ephemeris import (AnalyticEarthProvider, TableProvider, NovasDE421Provider
 from .jpleph import JPLEphemerisProvider
 from .problem import CompiledProblem, DeviceContext, fp64_peak
 from . import summary
-from .likelihood import Gaussianlikelihood, positions, set_default_earth_provider
+from .likelihood import Gaussianlikelihood, positions, positions_batch, set_default_earth_provider
 
 __all__ = [n for n in dir() if not n.startswith('_')]
 __version__ = '0.1.0'

@@ -906,7 +906,7 @@ int pick_plan(const StnCtx* ctx, int64_t n) {
     const int64_t slots_big = (int64_t)ctx->sm_count * minblocks_for(R);
     const int64_t tile_big = (int64_t)threads_for(R) * R;
     const int64_t tiles_big = (n + tile_big - 1) / tile_big;
-    if (tiles_big >= 8 * slots_big) return make_plan(1, 1);          // >= 8 waves: no split needed
+    if (tiles_big >= 32 * slots_big) return make_plan(1, 1);         // >= 32 waves: the last one is < 3 %
     // choose the number of splits that wastes the least of the last wave, given the tile count
     auto eff = [&](int64_t tiles, int64_t slots, int K) {
         const int64_t ctas = tiles * K;
@@ -923,7 +923,7 @@ int pick_plan(const StnCtx* ctx, int64_t n) {
             if (tiles_big * K < 2 * slots_big && K < T) continue;
             const double e = eff(tiles_big, slots_big, K);
             if (e > best * 1.02) { best = e; bestK = K; }
-            if (tiles_big * K >= 8 * slots_big) break;
+            if (tiles_big * K >= 32 * slots_big) break;
         }
         if (tiles_big * bestK >= 2 * slots_big) return make_plan(1, bestK);
     }

@@ -9,7 +9,7 @@ import collections
 import numpy as np
 
 from . import _lib
-from .constants import SENTINEL
+from .constants import SENTINEL, ROOTS
 from .problem import CompiledProblem, DeviceContext
 from .shares import filter_dictionary_of_parameter_with_index
 
@@ -318,6 +318,35 @@ def positions(refepoch, epochs, dict_timing, parameter_filter_index, dict_parame
     by_root = {_root_of(k): v for k, v in zip(keys, vals)}
     theta = np.array([[by_root[_root_of(n)] for n in like.parameter_names]], dtype=np.float64)
     return like.model_positions(theta, 0, mode=mode)[0]
+
+
+def positions_batch(refepoch, epochs, dict_timing, parameter_filter_index, names, samples, *,
+                    earth_provider=None, device=0, mode='fast'):
+    """positions() for MANY parameter vectors at once: the model curves the reference's sky plots
+    draw by calling positions() once per posterior draw on a dense epoch grid
+    (plot/sky_position_evolution.py:104-129, positions.py:240-264).
+
+    names / samples: column names and (n, len(names)) values (e.g. posterior draws); the
+    parameters of source `parameter_filter_index` are routed exactly as positions() routes a
+    dict.  Returns (n, 2E) = [ra(E)..., dec(E)...] in rad."""
+    from .readers import plain_timing
+    from .shares import column_table
+    samples = np.ascontiguousarray(samples, dtype=np.float64)
+    names = list(names)
+    epochs = np.ascontiguousarray(epochs, dtype=np.float64)
+    idx = column_table(names, parameter_filter_index + 1)[parameter_filter_index]
+    present = [bool(c >= 0) for c in idx]
+    shares = [[0] if on else [-1] for on in present]
+    shares[1], shares[2] = [-1], [-1]
+    E = epochs.shape[0]
+    vlbi = {'epochs': epochs, 'radecs': np.zeros(2 * E), 'errs': np.ones(2 * E)}
+    like = Gaussianlikelihood(refepoch, [plain_timing(dict_timing)], [vlbi], shares, None, None,
+                              earth_provider=earth_provider, device=device, mode=mode)
+    try:
+        cols = [int(idx[ROOTS.index(_root_of(n))]) for n in like.parameter_names]
+        return like.model_positions(samples[:, cols], 0, mode=mode)
+    finally:
+        like.close()
 
 
 def _root_of(name):

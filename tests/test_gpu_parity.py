@@ -446,3 +446,20 @@ def test_very_large_batch_indexing():
     like.close()
     del theta, out
     torch.cuda.empty_cache()
+
+
+def test_positions_batch_dense_grid():
+    """Model curves for many posterior draws on a dense epoch grid (the sky-plot workload)."""
+    case = synthetic.config4()
+    grid = np.linspace(57000.0, 57730.0, 301)
+    prov = sb.AnalyticEarthProvider()
+    xyz = sb.earth_vectors(prov, grid)
+    draws = case.sample_theta(500, seed=6, scale=0.1)
+    names, idx = O.column_table(case.shares)
+    for src in (0, 3):
+        got = sb.positions_batch(case.refepoch, grid, case.LoD_timing[src], src, case.names, draws,
+                                 earth_provider=prov, mode='strict')
+        vlbi = {'epochs': grid}
+        want, _ = O.batch_model(case.refepoch, vlbi, xyz, case.LoD_timing[src], idx[src], draws)
+        assert got.shape == (500, 602)
+        assert np.abs(got - want).max() <= 2 * np.spacing(6.3)
