@@ -334,7 +334,9 @@ def positions_batch(refepoch, epochs, dict_timing, parameter_filter_index, names
     samples = np.ascontiguousarray(samples, dtype=np.float64)
     names = list(names)
     epochs = np.ascontiguousarray(epochs, dtype=np.float64)
-    idx = column_table(names, parameter_filter_index + 1)[parameter_filter_index]
+    from .shares import parameter_name_to_pmparin_indice
+    n_sources = 1 + max([parameter_filter_index] + [i for n in names for i in parameter_name_to_pmparin_indice(n)[0]])
+    idx = column_table(names, n_sources)[parameter_filter_index]
     present = [bool(c >= 0) for c in idx]
     shares = [[0] if on else [-1] for on in present]
     shares[1], shares[2] = [-1], [-1]
