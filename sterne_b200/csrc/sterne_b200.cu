@@ -59,6 +59,9 @@
 #ifndef STN_CHUNK
 #define STN_CHUNK 128
 #endif
+#ifndef STN_PAIR_UNROLL
+#define STN_PAIR_UNROLL 1              /* unroll factor of the two-epoch loop body */
+#endif
 #ifndef STN_RCP_CUBIC
 #define STN_RCP_CUBIC 1            /* 1: cubic refinement of the reciprocal seed, 0: one Newton step */
 #endif
@@ -68,6 +71,7 @@ namespace {
 constexpr int kThreads = 256;      // threads per CTA of the likelihood kernels
 constexpr int kChunk = STN_CHUNK;  // epochs per shared-memory stage (128 * 96 B = 12 KiB)
 constexpr int kStages = 2;
+constexpr int kPairUnroll = STN_PAIR_UNROLL;
 constexpr int kFirst = 1, kLast = 2;
 
 struct SrcDev {
@@ -352,7 +356,7 @@ template <int R, int L, bool EF, bool BIN, bool SPLIT_EACH>
 __device__ __forceinline__ int epoch_loop(const double* __restrict__ rows, int n_epochs, int sub,
                                           const Coef (&cf)[R], Acc (&acc)[R]) {
     int e = sub;
-#pragma unroll 1
+#pragma unroll kPairUnroll
     for (; e + L < n_epochs; e += 2 * L) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
