@@ -440,8 +440,14 @@ __device__ double prior_terms(const ProbDev& P, const double* __restrict__ theta
 // ---------------------------------------------------------------------------------
 // K1: fused FAST log-likelihood
 // ---------------------------------------------------------------------------------
-__host__ __device__ constexpr int threads_for(int R) { return R > 2 ? STN_THREADS_R3 : kThreads; }
-__host__ __device__ constexpr int minblocks_for(int R) { return R > 2 ? STN_MINBLOCKS_R3 : 2; }
+#ifndef STN_THREADS_R2
+#define STN_THREADS_R2 256
+#endif
+#ifndef STN_MINBLOCKS_R2
+#define STN_MINBLOCKS_R2 2
+#endif
+__host__ __device__ constexpr int threads_for(int R) { return R > 2 ? STN_THREADS_R3 : (R == 2 ? STN_THREADS_R2 : kThreads); }
+__host__ __device__ constexpr int minblocks_for(int R) { return R > 2 ? STN_MINBLOCKS_R3 : (R == 2 ? STN_MINBLOCKS_R2 : 2); }
 
 template <int R, int L>
 __global__ void __launch_bounds__(threads_for(R), minblocks_for(R))
