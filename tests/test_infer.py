@@ -17,7 +17,7 @@ def test_argument_splitting_follows_the_reference():
 def test_inference_from_files_recovers_truth(tmp_path):
     case = synthetic.config2()                                   # EFAC, 6 parameters
     files = synthetic.write_case_files(case, str(tmp_path / 'in'))
-    prov = sb.TableProvider(case.LoD_VLBI[0]['epochs'] + 2400000.5, case.earth_xyz[0])
+    prov = sb.AnalyticEarthProvider()                            # the provider the synthetic data were made with
     res = infer.run(case.refepoch, files['inits'], files['pmparins'][0], files['parfiles'][0],
                     shares=case.shares, pmparin_preliminaries=files['preliminaries'], nwalkers=512,
                     iterations=1200, outdir=str(tmp_path / 'out'), earth_provider=prov, seed=3)
