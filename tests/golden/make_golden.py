@@ -234,6 +234,26 @@ def main():
     with open(os.path.join(HERE, 'golden_posterior_summary.json'), 'w') as f:
         json.dump(post, f)
     print('wrote golden_posterior_summary.json')
+    # read_parfile's substring keyword matching (reflex_motion.py:59-75): ECCDOT overwrites ECC,
+    # a KOM line matches 'OM ', EPS1/EPS2 are ignored, later lines win
+    quirky = ('PSRJ            J1234+5678\n'
+              'DECJ            -12:34:56.789               1  0.002\n'
+              'PB              12.3456789               1  0.0000001\n'
+              'ECC             0.1234               1  0.0001\n'
+              'ECCDOT          1.5e-15               1  1e-16\n'
+              'A1              9.8765               1  0.0001\n'
+              'A1DOT           2.5e-14               1  1e-15\n'
+              'T0              55555.5               1  0.01\n'
+              'OM              123.4               1  0.1\n'
+              'KOM             45.0               1  1.0\n'
+              'OMDOT           0.0123               1  0.001\n'
+              'PBDOT           1.2e-12               1  1e-13\n'
+              'OM_ASC          77.7               1  2.0\n'
+              'SINI            0.95               1  0.01\n')
+    with tempfile.TemporaryDirectory() as tmp:
+        qp = os.path.join(tmp, 'quirky.par')
+        open(qp, 'w').write(quirky)
+        out['parfile_quirks'] = {'text': quirky, 'ref': plain_timing(ref_reflex.read_parfile(qp))}
     path = os.path.join(HERE, 'golden_reference.json')
     with open(path, 'w') as f:
         json.dump(out, f)

@@ -164,3 +164,14 @@ def test_files_round_trip_to_memory_case(tmp_path):
         assert np.allclose(a['errs'], b['errs'], rtol=1e-10)
     timing = sb.create_list_of_dict_timing(f['parfiles'])
     assert timing[0]['pb'] == case.LoD_timing[0]['pb'] and timing[0]['a1'] == case.LoD_timing[0]['a1']
+
+
+def test_parfile_substring_quirks_match_reference(golden, tmp_path):
+    """reflex_motion.py:59-75 matches keywords by substring: an ECCDOT line overwrites ECC, a KOM line
+    sets OM.  Both the product reader and the oracle reader must reproduce that."""
+    q = golden['parfile_quirks']
+    p = tmp_path / 'quirky.par'
+    p.write_text(q['text'])
+    assert sb.read_parfile(str(p)) == q['ref']
+    assert O.read_parfile(str(p)) == q['ref']
+    assert q['ref']['ecc'] == 1.5e-15 and q['ref']['om'] == 45.0
