@@ -60,7 +60,10 @@
 #define STN_CHUNK 128
 #endif
 #ifndef STN_PAIR_UNROLL
-#define STN_PAIR_UNROLL 1              /* unroll factor of the two-epoch loop body */
+#define STN_PAIR_UNROLL 1              /* unroll factor of the two-epoch loop body, EFAC off */
+#endif
+#ifndef STN_PAIR_UNROLL_EFAC
+#define STN_PAIR_UNROLL_EFAC 2         /* same, EFAC on: measured 50.8 vs 51.7 ms (variant C) */
 #endif
 #ifndef STN_RCP_CUBIC
 #define STN_RCP_CUBIC 1            /* 1: cubic refinement of the reciprocal seed, 0: one Newton step */
@@ -72,6 +75,7 @@ constexpr int kThreads = 256;      // threads per CTA of the likelihood kernels
 constexpr int kChunk = STN_CHUNK;  // epochs per shared-memory stage (128 * 96 B = 12 KiB)
 constexpr int kStages = 2;
 constexpr int kPairUnroll = STN_PAIR_UNROLL;
+constexpr int kPairUnrollEfac = STN_PAIR_UNROLL_EFAC;
 constexpr int kFirst = 1, kLast = 2;
 
 struct SrcDev {
@@ -304,49 +308,80 @@ struct Acc {
     int esum;                 // EFAC: running sum of biased exponents taken out of prod
 };
 
-// One epoch of one sample.  EF: the two variances are multiplied into acc.prod
-// (SPLIT_EACH: with an exponent extraction after each, for tables whose variances are
-// so extreme that a product of a few of them could leave the double range).
-template <bool EF, bool BIN, bool SPLIT_EACH>
-__device__ __forceinline__ void epoch_term(const double* __restrict__ rows, int e, const Coef& cf, Acc& acc) {
+// Residuals of one epoch of one sample, and for EFAC sources the two variances.
+template <bool EF, bool BIN>
+__device__ __forceinline__ void epoch_residuals(const double* __restrict__ rows, int e, const Coef& cf,
+                                                double& res_ra, double& res_dec, double& v_ra, double& v_dec,
+                                                double2& aa) {
     const double2* row = reinterpret_cast<const double2*>(rows + e * STN_FAST_ROW);
     const double2 tx = row[0];
     const double2 yz = row[1];
     const double2 ob = row[2];
-    const double2 aa = row[3];
+    aa = row[3];
     double2 bc = make_double2(0.0, 0.0);
     if (BIN) bc = row[5];
     double ora, odec;
     fast_offsets<BIN>(cf, tx, yz, bc, ora, odec);
     // model = ref + offset (rad); residual = obs - model   (positions.py:119-120,
     // simulate.py:368).  This order is kept: the subtraction cancels ~9 digits.
-    const double res_ra = ob.x - (cf.ra + ora);
-    const double res_dec = ob.y - (cf.dec + odec);
+    res_ra = ob.x - (cf.ra + ora);
+    res_dec = ob.y - (cf.dec + odec);
+    if (EF) {
+        const double2 bb = row[4];
+        v_ra = fma(cf.g_ra, bb.x, aa.x);                  // simulate.py:317
+        v_dec = fma(cf.g_dec, bb.y, aa.y);
+    }
+}
+
+// One epoch of one sample.  EFAC: r_a^2/v_a + r_d^2/v_d = (r_a^2 v_d + r_d^2 v_a) / (v_a v_d) costs one
+// reciprocal, and the product p = v_a v_d is also the epoch's factor of the log-determinant.
+// SPLIT_EACH (tables whose variances could leave the double range when multiplied): one reciprocal
+// and one exponent extraction per variance.
+template <bool EF, bool BIN, bool SPLIT_EACH>
+__device__ __forceinline__ void epoch_term(const double* __restrict__ rows, int e, const Coef& cf, Acc& acc) {
+    double res_ra, res_dec, v_ra = 1.0, v_dec = 1.0;
+    double2 aa;
+    epoch_residuals<EF, BIN>(rows, e, cf, res_ra, res_dec, v_ra, v_dec, aa);
     if (!EF) {
         const double z_ra = res_ra * aa.x;
         const double z_dec = res_dec * aa.y;
         acc.chi_ra = fma(z_ra, z_ra, acc.chi_ra);
         acc.chi_dec = fma(z_dec, z_dec, acc.chi_dec);
+    } else if (SPLIT_EACH) {
+        acc.chi_ra = fma(res_ra * res_ra, fast_rcp(v_ra), acc.chi_ra);
+        acc.chi_dec = fma(res_dec * res_dec, fast_rcp(v_dec), acc.chi_dec);
+        acc.prod = split_exp(acc.prod * v_ra, acc.esum);
+        acc.prod = split_exp(acc.prod * v_dec, acc.esum);
     } else {
-        const double2 bb = row[4];
-        const double v_ra = fma(cf.g_ra, bb.x, aa.x);     // simulate.py:317
-        const double v_dec = fma(cf.g_dec, bb.y, aa.y);
-        if (SPLIT_EACH) {
-            acc.chi_ra = fma(res_ra * res_ra, fast_rcp(v_ra), acc.chi_ra);
-            acc.chi_dec = fma(res_dec * res_dec, fast_rcp(v_dec), acc.chi_dec);
-            acc.prod = split_exp(acc.prod * v_ra, acc.esum);
-            acc.prod = split_exp(acc.prod * v_dec, acc.esum);
-        } else {
-            // one reciprocal for both coordinates: r_a^2/v_a + r_d^2/v_d = (r_a^2 v_d + r_d^2 v_a)/(v_a v_d);
-            // the product v_a v_d is also this epoch's factor of the log-determinant
-            const double p = v_ra * v_dec;
-            const double w = fast_rcp(p);
-            double s = (res_ra * res_ra) * v_dec;
-            s = fma(res_dec * res_dec, v_ra, s);
-            acc.chi_ra = fma(s, w, acc.chi_ra);
-            acc.prod *= p;
-        }
+        const double p = v_ra * v_dec;
+        double s = (res_ra * res_ra) * v_dec;
+        s = fma(res_dec * res_dec, v_ra, s);
+        acc.chi_ra = fma(s, fast_rcp(p), acc.chi_ra);
+        acc.prod = split_exp(acc.prod * p, acc.esum);
     }
+}
+
+// Two epochs of one EFAC sample with ONE reciprocal for all four variances:
+//   s_a/p_a + s_b/p_b = (s_a p_b + s_b p_a) / (p_a p_b),   p = v_ra v_dec,  s = r_ra^2 v_dec + r_dec^2 v_ra
+// and p_a p_b is the pair's factor of the log-determinant (one exponent extraction per pair).
+template <bool BIN>
+__device__ __forceinline__ void epoch_pair_efac(const double* __restrict__ rows, int ea, int eb, const Coef& cf,
+                                                Acc& acc) {
+    double ra_a, dec_a, vra_a, vdec_a, ra_b, dec_b, vra_b, vdec_b;
+    double2 aa;
+    epoch_residuals<true, BIN>(rows, ea, cf, ra_a, dec_a, vra_a, vdec_a, aa);
+    const double p_a = vra_a * vdec_a;
+    double s_a = (ra_a * ra_a) * vdec_a;
+    s_a = fma(dec_a * dec_a, vra_a, s_a);
+    epoch_residuals<true, BIN>(rows, eb, cf, ra_b, dec_b, vra_b, vdec_b, aa);
+    const double p_b = vra_b * vdec_b;
+    double s_b = (ra_b * ra_b) * vdec_b;
+    s_b = fma(dec_b * dec_b, vra_b, s_b);
+    const double p4 = p_a * p_b;
+    double t = s_a * p_b;
+    t = fma(s_b, p_a, t);
+    acc.chi_ra = fma(t, fast_rcp(p4), acc.chi_ra);
+    acc.prod = split_exp(acc.prod * p4, acc.esum);
 }
 
 // Returns the number of exponent extractions made per sample (the same for every sample
@@ -356,21 +391,24 @@ template <int R, int L, bool EF, bool BIN, bool SPLIT_EACH>
 __device__ __forceinline__ int epoch_loop(const double* __restrict__ rows, int n_epochs, int sub,
                                           const Coef (&cf)[R], Acc (&acc)[R]) {
     int e = sub;
-#pragma unroll kPairUnroll
+    // the deeper unroll only pays in the R = 3 kernel (EFAC problems); in the 128-register R <= 2
+    // kernels it costs spills that also slow their non-EFAC loops
+    constexpr int kUnroll = (EF && !SPLIT_EACH && R >= 3) ? kPairUnrollEfac : kPairUnroll;
+#pragma unroll kUnroll
     for (; e + L < n_epochs; e += 2 * L) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            epoch_term<EF, BIN, SPLIT_EACH>(rows, e, cf[r], acc[r]);
-            epoch_term<EF, BIN, SPLIT_EACH>(rows, e + L, cf[r], acc[r]);
-            if (EF && !SPLIT_EACH) acc[r].prod = split_exp(acc[r].prod, acc[r].esum);
+            if (EF && !SPLIT_EACH) {
+                epoch_pair_efac<BIN>(rows, e, e + L, cf[r], acc[r]);
+            } else {
+                epoch_term<EF, BIN, SPLIT_EACH>(rows, e, cf[r], acc[r]);
+                epoch_term<EF, BIN, SPLIT_EACH>(rows, e + L, cf[r], acc[r]);
+            }
         }
     }
     if (e < n_epochs) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            epoch_term<EF, BIN, SPLIT_EACH>(rows, e, cf[r], acc[r]);
-            if (EF && !SPLIT_EACH) acc[r].prod = split_exp(acc[r].prod, acc[r].esum);
-        }
+        for (int r = 0; r < R; ++r) epoch_term<EF, BIN, SPLIT_EACH>(rows, e, cf[r], acc[r]);
     }
     // epochs handled by this lane: sub, sub+L, ...
     const int cnt = sub < n_epochs ? (n_epochs - sub + L - 1) / L : 0;
@@ -1113,7 +1151,7 @@ int stn_create(const StnProblem* pb, int device, StnCtx** out_ctx) {
                 for (int k = 6; k < 8; ++k) { if (row[k] < a_min) a_min = row[k]; if (row[k] > a_max) a_max = row[k]; }
                 for (int k = 8; k < 10; ++k) if (row[k] > b_max) b_max = row[k];
             }
-            d.grouped = (hs.n_epochs > 0 && a_min >= 1e-60 && a_max <= 1e60 && b_max <= 1e30) ? 1 : 0;
+            d.grouped = (hs.n_epochs > 0 && a_min >= 1e-60 && a_max <= 1e30 && b_max <= 1e15) ? 1 : 0;
         }
         d.cos_decj = hs.binary ? hs.cos_decj : 1.0;
         d.inv_cos_decj = 1.0 / d.cos_decj;
