@@ -65,6 +65,9 @@
 #ifndef STN_PAIR_UNROLL_EFAC
 #define STN_PAIR_UNROLL_EFAC 2         /* same, EFAC on: measured 50.8 vs 51.7 ms (variant C) */
 #endif
+#ifndef STN_QUAD_EFAC
+#define STN_QUAD_EFAC 1                /* EFAC: one reciprocal per four epochs (else per two) */
+#endif
 #ifndef STN_RCP_CUBIC
 #define STN_RCP_CUBIC 1            /* 1: cubic refinement of the reciprocal seed, 0: one Newton step */
 #endif
@@ -361,39 +364,77 @@ __device__ __forceinline__ void epoch_term(const double* __restrict__ rows, int 
     }
 }
 
+// (s, p) of one EFAC epoch: s = r_ra^2 v_dec + r_dec^2 v_ra, p = v_ra v_dec, so that the epoch's
+// chi-square contribution is s / p and its log-determinant factor is p.
+template <bool BIN>
+__device__ __forceinline__ void epoch_sp(const double* __restrict__ rows, int e, const Coef& cf, double& s,
+                                         double& p) {
+    double res_ra, res_dec, v_ra, v_dec;
+    double2 aa;
+    epoch_residuals<true, BIN>(rows, e, cf, res_ra, res_dec, v_ra, v_dec, aa);
+    p = v_ra * v_dec;
+    s = (res_ra * res_ra) * v_dec;
+    s = fma(res_dec * res_dec, v_ra, s);
+}
+
 // Two epochs of one EFAC sample with ONE reciprocal for all four variances:
-//   s_a/p_a + s_b/p_b = (s_a p_b + s_b p_a) / (p_a p_b),   p = v_ra v_dec,  s = r_ra^2 v_dec + r_dec^2 v_ra
-// and p_a p_b is the pair's factor of the log-determinant (one exponent extraction per pair).
+//   s_a/p_a + s_b/p_b = (s_a p_b + s_b p_a) / (p_a p_b)
+// and p_a p_b is the pair's factor of the log-determinant.  (t, q) = (numerator, denominator).
+template <bool BIN>
+__device__ __forceinline__ void epoch_pair_tq(const double* __restrict__ rows, int ea, int eb, const Coef& cf,
+                                              double& t, double& q) {
+    double s_a, p_a, s_b, p_b;
+    epoch_sp<BIN>(rows, ea, cf, s_a, p_a);
+    epoch_sp<BIN>(rows, eb, cf, s_b, p_b);
+    q = p_a * p_b;
+    t = s_a * p_b;
+    t = fma(s_b, p_a, t);
+}
+
 template <bool BIN>
 __device__ __forceinline__ void epoch_pair_efac(const double* __restrict__ rows, int ea, int eb, const Coef& cf,
                                                 Acc& acc) {
-    double ra_a, dec_a, vra_a, vdec_a, ra_b, dec_b, vra_b, vdec_b;
-    double2 aa;
-    epoch_residuals<true, BIN>(rows, ea, cf, ra_a, dec_a, vra_a, vdec_a, aa);
-    const double p_a = vra_a * vdec_a;
-    double s_a = (ra_a * ra_a) * vdec_a;
-    s_a = fma(dec_a * dec_a, vra_a, s_a);
-    epoch_residuals<true, BIN>(rows, eb, cf, ra_b, dec_b, vra_b, vdec_b, aa);
-    const double p_b = vra_b * vdec_b;
-    double s_b = (ra_b * ra_b) * vdec_b;
-    s_b = fma(dec_b * dec_b, vra_b, s_b);
-    const double p4 = p_a * p_b;
-    double t = s_a * p_b;
-    t = fma(s_b, p_a, t);
-    acc.chi_ra = fma(t, fast_rcp(p4), acc.chi_ra);
-    acc.prod = split_exp(acc.prod * p4, acc.esum);
+    double t, q;
+    epoch_pair_tq<BIN>(rows, ea, eb, cf, t, q);
+    acc.chi_ra = fma(t, fast_rcp(q), acc.chi_ra);
+    acc.prod = split_exp(acc.prod * q, acc.esum);
 }
 
-// Returns the number of exponent extractions made per sample (the same for every sample
-// of the thread).  !SPLIT_EACH: one extraction per two epochs (four variances); the host
-// enables it only when four variances cannot overflow / underflow (see stn_create).
-template <int R, int L, bool EF, bool BIN, bool SPLIT_EACH>
+// Four epochs, eight variances, one reciprocal and one exponent extraction.
+template <bool BIN>
+__device__ __forceinline__ void epoch_quad_efac(const double* __restrict__ rows, int e, int step, const Coef& cf,
+                                                Acc& acc) {
+    double t1, q1, t2, q2;
+    epoch_pair_tq<BIN>(rows, e, e + step, cf, t1, q1);
+    epoch_pair_tq<BIN>(rows, e + 2 * step, e + 3 * step, cf, t2, q2);
+    const double q = q1 * q2;
+    double t = t1 * q2;
+    t = fma(t2, q1, t);
+    acc.chi_ra = fma(t, fast_rcp(q), acc.chi_ra);
+    acc.prod = split_exp(acc.prod * q, acc.esum);
+}
+
+// Returns the number of exponent extractions made per sample (the same for every sample of
+// the thread).  !SPLIT_EACH: one extraction per four epochs (eight variances), then per pair and
+// per single epoch for the remainder; the host enables it only when eight variances cannot
+// overflow / underflow (see stn_create).
+template <int R, int L, bool QUAD, bool EF, bool BIN, bool SPLIT_EACH>
 __device__ __forceinline__ int epoch_loop(const double* __restrict__ rows, int n_epochs, int sub,
                                           const Coef (&cf)[R], Acc (&acc)[R]) {
     int e = sub;
+    // QUAD is a property of the PROBLEM (EFAC-heavy or not), never of the batch size: the grouping
+    // of the reciprocal changes rounding, and a sample's bits must not depend on R or on sharding
+    constexpr bool kQuad = EF && !SPLIT_EACH && QUAD;
+    if (kQuad) {
+#pragma unroll 1
+        for (; e + 3 * L < n_epochs; e += 4 * L) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) epoch_quad_efac<BIN>(rows, e, L, cf[r], acc[r]);
+        }
+    }
     // the deeper unroll only pays in the R = 3 kernel (EFAC problems); in the 128-register R <= 2
     // kernels it costs spills that also slow their non-EFAC loops
-    constexpr int kUnroll = (EF && !SPLIT_EACH && R >= 3) ? kPairUnrollEfac : kPairUnroll;
+    constexpr int kUnroll = (EF && !SPLIT_EACH && R >= 3 && !kQuad) ? kPairUnrollEfac : kPairUnroll;
 #pragma unroll kUnroll
     for (; e + L < n_epochs; e += 2 * L) {
 #pragma unroll
@@ -412,7 +453,11 @@ __device__ __forceinline__ int epoch_loop(const double* __restrict__ rows, int n
     }
     // epochs handled by this lane: sub, sub+L, ...
     const int cnt = sub < n_epochs ? (n_epochs - sub + L - 1) / L : 0;
-    return !EF ? 0 : (SPLIT_EACH ? 2 * cnt : (cnt + 1) / 2);
+    if (!EF) return 0;
+    if (SPLIT_EACH) return 2 * cnt;
+    const int quads = kQuad ? cnt / 4 : 0;
+    const int rem = cnt - 4 * quads;
+    return quads + (rem + 1) / 2;
 }
 
 template <int L>
@@ -487,7 +532,7 @@ __device__ double prior_terms(const ProbDev& P, const double* __restrict__ theta
 __host__ __device__ constexpr int threads_for(int R) { return R > 2 ? STN_THREADS_R3 : (R == 2 ? STN_THREADS_R2 : kThreads); }
 __host__ __device__ constexpr int minblocks_for(int R) { return R > 2 ? STN_MINBLOCKS_R3 : (R == 2 ? STN_MINBLOCKS_R2 : 2); }
 
-template <int R, int L>
+template <int R, int L, bool QUAD>
 __global__ void __launch_bounds__(threads_for(R), minblocks_for(R))
 stn_loglike_fast_kernel(const ProbDev P, const double* __restrict__ theta, const int64_t N,
                         const int64_t ld, const int layout, double* __restrict__ out,
@@ -562,12 +607,12 @@ stn_loglike_fast_kernel(const ProbDev P, const double* __restrict__ theta, const
         const bool bin = S.binary != 0;
         const bool grouped = S.grouped != 0;
         if (first) nsplit = 0;
-        if (!ef && !bin) epoch_loop<R, L, false, false, false>(rows, ck.n_epochs, sub, cf, acc);
-        else if (!ef && bin) epoch_loop<R, L, false, true, false>(rows, ck.n_epochs, sub, cf, acc);
-        else if (ef && !bin && grouped) nsplit += epoch_loop<R, L, true, false, false>(rows, ck.n_epochs, sub, cf, acc);
-        else if (ef && bin && grouped) nsplit += epoch_loop<R, L, true, true, false>(rows, ck.n_epochs, sub, cf, acc);
-        else if (ef && !bin) nsplit += epoch_loop<R, L, true, false, true>(rows, ck.n_epochs, sub, cf, acc);
-        else nsplit += epoch_loop<R, L, true, true, true>(rows, ck.n_epochs, sub, cf, acc);
+        if (!ef && !bin) epoch_loop<R, L, QUAD, false, false, false>(rows, ck.n_epochs, sub, cf, acc);
+        else if (!ef && bin) epoch_loop<R, L, QUAD, false, true, false>(rows, ck.n_epochs, sub, cf, acc);
+        else if (ef && !bin && grouped) nsplit += epoch_loop<R, L, QUAD, true, false, false>(rows, ck.n_epochs, sub, cf, acc);
+        else if (ef && bin && grouped) nsplit += epoch_loop<R, L, QUAD, true, true, false>(rows, ck.n_epochs, sub, cf, acc);
+        else if (ef && !bin) nsplit += epoch_loop<R, L, QUAD, true, false, true>(rows, ck.n_epochs, sub, cf, acc);
+        else nsplit += epoch_loop<R, L, QUAD, true, true, true>(rows, ck.n_epochs, sub, cf, acc);
 
         if (last) {
 #pragma unroll
@@ -995,7 +1040,7 @@ int pick_plan(const StnCtx* ctx, int64_t n) {
     return make_plan(L, K);
 }
 
-template <int R, int L>
+template <int R, int L, bool QUAD>
 int launch_fast(StnCtx* ctx, const ProbDev& prob, const double* theta, int64_t n, int64_t ld, int layout,
                 double* out, cudaStream_t st, int splits, double* partial) {
     constexpr int per_cta = (threads_for(R) / L) * R;
@@ -1003,7 +1048,7 @@ int launch_fast(StnCtx* ctx, const ProbDev& prob, const double* theta, int64_t n
     if (grid > 0x7fffffffLL) return fail(STN_ERR_INVALID, "batch too large for one launch");
     dim3 g((unsigned)grid, (unsigned)splits, 1);
     (void)cudaGetLastError();      // other CUDA users of this process (torch) may have left a stale error
-    stn_loglike_fast_kernel<R, L><<<g, threads_for(R), 0, st>>>(prob, theta, n, ld, layout, out, partial);
+    stn_loglike_fast_kernel<R, L, QUAD><<<g, threads_for(R), 0, st>>>(prob, theta, n, ld, layout, out, partial);
     STN_CUDA(cudaGetLastError());
     ctx->launches++;
     if (splits > 1) {
@@ -1054,11 +1099,20 @@ int launch_loglike(StnCtx* ctx, const double* theta, int64_t n, int64_t ld, int 
         partial = ctx->scratch[scratch_slot];
     }
     const int R = choose_R(ctx, n, lanes, splits);
-#define STN_GO(RR, LL) return launch_fast<RR, LL>(ctx, prob, theta, n, ld, layout, out, st, splits, partial)
+    // EFAC-heavy problems: big kernel R = STN_RBIG_EFAC, reciprocal shared by four epochs (QUAD);
+    // other problems: big kernel R = STN_RBIG, reciprocal shared by two epochs
+    const bool quad = ctx->efac_heavy && STN_QUAD_EFAC;
+#define STN_GO(RR, LL)                                                                                          \
+    do {                                                                                                        \
+        if (quad) return launch_fast<RR, LL, true>(ctx, prob, theta, n, ld, layout, out, st, splits, partial);  \
+        return launch_fast<RR, LL, false>(ctx, prob, theta, n, ld, layout, out, st, splits, partial);           \
+    } while (0)
     switch (lanes) {
         case 1:
-            if (R == STN_RBIG_EFAC && STN_RBIG_EFAC != STN_RBIG) STN_GO(STN_RBIG_EFAC, 1);
-            if (R == STN_RBIG) STN_GO(STN_RBIG, 1);
+            if (R > 1) {
+                if (quad) return launch_fast<STN_RBIG_EFAC, 1, true>(ctx, prob, theta, n, ld, layout, out, st, splits, partial);
+                return launch_fast<STN_RBIG, 1, false>(ctx, prob, theta, n, ld, layout, out, st, splits, partial);
+            }
             STN_GO(1, 1);
         case 2: STN_GO(1, 2);
         case 4: STN_GO(1, 4);
@@ -1143,15 +1197,16 @@ int stn_create(const StnProblem* pb, int device, StnCtx** out_ctx) {
         d.grouped = 0;
         if (d.efac_on) {
             // variance v = a + g*b with a = err_random^2, b = err_sys^2, g = efac^2 >= 0:
-            // v >= a_min, and v^4 stays far inside the double range for any efac below ~1e45
-            // when the table is within these bounds (radians-scale errors are ~1e-19..1e-9).
+            // v >= a_min, and v^8 (the product of the eight variances of four epochs) stays inside the
+            // double range for any efac below ~1e11 when the table is within these bounds
+            // (squared radians-scale errors are ~1e-19).
             double a_min = 1e300, a_max = 0.0, b_max = 0.0;
             for (int64_t e = 0; e < hs.n_epochs; ++e) {
                 const double* row = hs.fast_rows + e * STN_FAST_ROW;
                 for (int k = 6; k < 8; ++k) { if (row[k] < a_min) a_min = row[k]; if (row[k] > a_max) a_max = row[k]; }
                 for (int k = 8; k < 10; ++k) if (row[k] > b_max) b_max = row[k];
             }
-            d.grouped = (hs.n_epochs > 0 && a_min >= 1e-60 && a_max <= 1e30 && b_max <= 1e15) ? 1 : 0;
+            d.grouped = (hs.n_epochs > 0 && a_min >= 1e-30 && a_max <= 1e30 && b_max <= 1e15) ? 1 : 0;
         }
         d.cos_decj = hs.binary ? hs.cos_decj : 1.0;
         d.inv_cos_decj = 1.0 / d.cos_decj;
