@@ -329,8 +329,8 @@ def run_ours(args, rank, local_rank, world):
                 'frac': achieved_tf / peak_tf,
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` capture of this
                 # command (profiles/r01_ncu_loglike_fast_C.txt); algorithmic bytes per launch are alg_bytes below
-                'traffic': 745865984 + 35155712, 'traffic_unit': 'bytes per launch', 'algorithmic_bytes': alg_bytes,
-                'kernel': 'stn_loglike_fast_kernel<3,1>', 'kernel_ms': kernel_ms,
+                'traffic': 744556800 + 35271424, 'traffic_unit': 'bytes per launch', 'algorithmic_bytes': alg_bytes,
+                'kernel': 'stn_loglike_fast_kernel<3,1,true>', 'kernel_ms': kernel_ms,
                 'flops_per_eval': FLOPS_PER_EVAL['C'],
                 'peak_source': 'stn_fp64_peak DFMA micro-benchmark in this run (MEASURED_PEAKS.json has no FP64 '
                                'figure); nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2',
