@@ -190,7 +190,9 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
 
-    N = 1 << LOG2_N
+    # weak scaling (default, the contract's): 2^22 vectors per GPU.  --scaling strong: 2^22 vectors in
+    # total, 2^22 / world per GPU (SURVEY 8e's reading of the 1 -> 8 GPU target).
+    N = (1 << LOG2_N) if args.scaling == 'weak' else (1 << LOG2_N) // world
     case = synthetic.config5('C')
     like = case.likelihood(device=local_rank)
     ctx = like._context(None)
@@ -315,8 +317,8 @@ def run_ours(args, rank, local_rank, world):
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': workload_config(world),
+            'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': dict(workload_config(world), samples_per_gpu=N),
             'clocks': clocks,
             'e2e': {'value': world * evals_per_step_rank * e2e_steps / (e2e_ms * 1e-3), 'unit': UNIT,
                     'h2d_bytes_per_step': world * N * case.n_params * 8, 'd2h_bytes_per_step': world * N * 8,
@@ -355,6 +357,7 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'])
     ap.add_argument('--cpu-rows', type=int, default=0,
                     help='parameter vectors in the bounded CPU sample (0: calibrate to ~10-15 s of wall time)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
