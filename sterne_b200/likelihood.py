@@ -269,6 +269,17 @@ class Gaussianlikelihood(_LikelihoodBase):
             off = off.cpu().numpy() if offsets else None
         return (radec, off) if offsets else radec
 
+    # bilby pickles the likelihood (resume files, npool > 1): device handles are dropped and the
+    # contexts are rebuilt lazily in whichever process touches the object next
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state['_contexts'] = {}
+        state['_one'] = None
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+
     def close(self):
         seen = set()
         for ctx in self._contexts.values():

@@ -426,3 +426,19 @@ def test_positions_batch_dense_grid():
         want, _ = O.batch_model(case.refepoch, vlbi, xyz, case.LoD_timing[src], idx[src], draws)
         assert got.shape == (500, 602)
         assert np.abs(got - want).max() <= 2 * np.spacing(6.3)
+
+
+def test_likelihood_survives_pickling():
+    """bilby pickles the likelihood (resume files, worker pools): handles are dropped, contexts rebuilt."""
+    import pickle
+    case = synthetic.config3('dots')
+    like = case.likelihood()
+    theta = case.sample_theta(64, seed=1)
+    want = like.log_likelihood_batch(theta)
+    like.parameters.update(dict(zip(case.names, theta[0])))
+    clone = pickle.loads(pickle.dumps(like))
+    assert clone._contexts == {} and clone.parameters == like.parameters
+    assert np.array_equal(clone.log_likelihood_batch(theta), want)
+    assert clone.log_likelihood() == like.log_likelihood()
+    clone.close()
+    like.close()
