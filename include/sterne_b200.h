@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define STN_ABI_VERSION 1
+#define STN_ABI_VERSION 2
 
 /* Parameter roots in the reference's fixed alphabetical order
  * (priors.py:270, positions.py:56).  StnSource.col[] is indexed by these. */
@@ -70,7 +70,7 @@ enum StnMode {
 
 /* Per-epoch row of the STRICT table: STN_STRICT_ROW doubles.
  *  [0] dT [1] X [2] Y [3] Z [4] obs RA [5] obs Dec
- *  [6] err_ra [7] err_dec                    (EFAC off: VLBI 'errs')
+ *  [6] err_ra [7] err_dec                    (VLBI 'errs'; also used when efac is sampled as -999)
  *  [8] err_random_ra [9] err_random_dec [10] err_sys_ra [11] err_sys_dec   (EFAC on)
  *  [12] b_AU [13] cos(theta) [14] sin(theta) [15] unused
  */
@@ -179,9 +179,41 @@ int stn_auto_plan(StnCtx* ctx, int64_t n);
 /* Number of kernel launches issued through this context so far. */
 int64_t stn_launch_count(StnCtx* ctx);
 
-/* Pinned host memory for the *_host entry points. */
+/* Pinned host memory for the *_host entry points (portable: every device can DMA from it).
+ * stn_host_register pins a buffer the caller already owns (e.g. a sampler's numpy array) in
+ * place; pageable buffers are accepted too and are staged through the library's own pinned ring. */
 int stn_host_alloc(void** ptr, int64_t bytes);
 int stn_host_free(void* ptr);
+int stn_host_register(void* ptr, int64_t bytes);
+int stn_host_unregister(void* ptr);
+
+/* ---- several GPUs of one box driven from ONE process ---------------------------
+ * The reference is one process with one sampler (simulate.py:191-192) that owns one (N, P)
+ * batch; these entry points let that process use every GPU.  Each device holds the full epoch
+ * tables; the batch is cut into contiguous slices (stn_multi_slice), one per device.  There is
+ * no collective: every device DMAs its slice of log L straight into the caller's host array
+ * (stn_multi_loglike_host), or, for device-resident slices, into one device buffer with peer
+ * copies over NVLink (stn_multi_loglike_dev).  The execution plan is chosen from the WHOLE batch,
+ * so a vector's log L has the same bits whatever the number of devices.  `devices` may name a
+ * device more than once (two contexts on one GPU). */
+typedef struct StnMulti StnMulti;
+int stn_multi_create(const StnProblem* problem, const int* devices, int n_devices, StnMulti** out);
+int stn_multi_destroy(StnMulti* m);
+int stn_multi_size(StnMulti* m);
+StnCtx* stn_multi_ctx(StnMulti* m, int i);           /* borrowed: context of the i-th device */
+int64_t stn_multi_launch_count(StnMulti* m);
+/* [lo, hi) of part `part` of n rows cut into n_parts contiguous slices (the first n % n_parts
+ * slices hold one extra row). */
+int stn_multi_slice(int64_t n, int n_parts, int part, int64_t* lo, int64_t* hi);
+/* Same contract as stn_loglike_host; slices below 2^15 rows are not worth a device, so small
+ * batches use fewer devices (down to one).  One host thread per device used. */
+int stn_multi_loglike_host(StnMulti* m, const double* theta_host, int64_t n, int64_t ld,
+                           int layout, int mode, int plan, double* out_host);
+/* theta_dev[g]: counts[g] vectors resident on the g-th device (same ld / layout for all);
+ * out_dev: sum(counts) doubles on device `out_device`, slices in device order.  Synchronous. */
+int stn_multi_loglike_dev(StnMulti* m, const double* const* theta_dev, const int64_t* counts,
+                          int64_t ld, int layout, int mode, int plan, double* out_dev,
+                          int out_device);
 
 /* FP64 pipe peak (dependent-free DFMA streams on every SM); the roofline denominator.
  * Runs `reps` launches of `iters` FMA rounds, returns the best TFLOP/s and its time. */

@@ -13,7 +13,7 @@ from .readers import (readpmparin, create_list_of_dict_VLBI, read_parfile, creat
                       read_inits, dms2deg, dms_str2deg, decyear2mjd)
 from .ephemeris import (AnalyticEarthProvider, TableProvider, NovasDE421Provider, earth_vectors)
 from .jpleph import JPLEphemerisProvider
-from .problem import CompiledProblem, DeviceContext, fp64_peak
+from .problem import CompiledProblem, DeviceContext, MultiDeviceContext, host_register, fp64_peak
 from . import summary
 from .likelihood import Gaussianlikelihood, positions, positions_batch, set_default_earth_provider
 

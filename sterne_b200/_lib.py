@@ -81,7 +81,19 @@ SYMBOLS = [
     ('stn_stretch_accept', _int, [_int, _vp, _vp, _i64, ctypes.c_int32, _i64, _int, ctypes.c_uint64, ctypes.c_uint64,
                                   _vp, _vp, _vp, _vp, _vp]),
     ('stn_loglike_timed', _int, [_vp, _vp, _i64, _i64, _int, _int, _int, _vp, _int, c_double_p]),
+    ('stn_host_register', _int, [_vp, _i64]),
+    ('stn_host_unregister', _int, [_vp]),
+    ('stn_multi_create', _int, [ctypes.POINTER(StnProblem), c_int32_p, _int, ctypes.POINTER(_vp)]),
+    ('stn_multi_destroy', _int, [_vp]),
+    ('stn_multi_size', _int, [_vp]),
+    ('stn_multi_ctx', _vp, [_vp, _int]),
+    ('stn_multi_launch_count', _i64, [_vp]),
+    ('stn_multi_slice', _int, [_i64, _int, _int, ctypes.POINTER(_i64), ctypes.POINTER(_i64)]),
+    ('stn_multi_loglike_host', _int, [_vp, _vp, _i64, _i64, _int, _int, _int, _vp]),
+    ('stn_multi_loglike_dev', _int, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_i64), _i64, _int, _int, _int, _vp,
+                                     _int]),
 ]
+ABI_VERSION = 2
 
 
 class StnError(RuntimeError):
@@ -117,6 +129,9 @@ def load(build_if_missing=True):
         fn = getattr(lib, name)            # AttributeError if the ABI is incomplete
         fn.restype = restype
         fn.argtypes = argtypes
+    if lib.stn_version() != ABI_VERSION:
+        raise StnError('%s has ABI version %d, this package binds version %d; rebuild with '
+                       '`python -m sterne_b200.build --force`' % (path, lib.stn_version(), ABI_VERSION))
     _lib = lib
     return lib
 

@@ -41,7 +41,20 @@ def build_library(force=False, verbose=False, extra=(), out=None):
     return out or LIB
 
 
+DEBUG_LIB = os.path.join(ROOT, 'build_variants', 'libsterne_b200_debug.so')
+
+
+def build_debug_library(verbose=False):
+    """The bounds-asserting build (-DSTN_DEBUG, see csrc/sterne_b200.cu): select it with
+    STERNE_B200_LIB=build_variants/libsterne_b200_debug.so."""
+    os.makedirs(os.path.dirname(DEBUG_LIB), exist_ok=True)
+    return build_library(force=True, verbose=verbose, extra=['-DSTN_DEBUG', '-lcuda'], out=DEBUG_LIB)
+
+
 if __name__ == '__main__':
-    build_library(force='--force' in sys.argv, verbose=True,
-                  extra=['-Xptxas', '-v'] if '--ptxas-v' in sys.argv else [])
-    print(LIB)
+    if '--debug' in sys.argv:
+        print(build_debug_library(verbose=True))
+    else:
+        build_library(force='--force' in sys.argv, verbose=True,
+                      extra=['-Xptxas', '-v'] if '--ptxas-v' in sys.argv else [])
+        print(LIB)

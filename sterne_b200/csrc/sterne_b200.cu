@@ -23,12 +23,24 @@
 
 #include <cuda_runtime.h>
 #include <math_constants.h>
+// -DSTN_DEBUG (python -m sterne_b200.build --debug): device-side asserts on every index the kernels
+// form, and host-side checks that every device buffer a launch is given (the caller's and the
+// library's own) lies inside ONE allocation of sufficient size (cuMemGetAddressRange).  This pool
+// has no compute-sanitizer; the GPU test-suite is run once under this build instead.
+#ifdef STN_DEBUG
+#include <cuda.h>
+#include <cassert>
+#define STN_ASSERT(x) assert(x)
+#else
+#define STN_ASSERT(x) ((void)0)
+#endif
 #include <cstdio>
 #include <cstdarg>
 #include <cstring>
 #include <cmath>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 // ---------------------------------------------------------------------------------
@@ -62,14 +74,13 @@
 #ifndef STN_PAIR_UNROLL
 #define STN_PAIR_UNROLL 1              /* unroll factor of the two-epoch loop body, EFAC off */
 #endif
-#ifndef STN_PAIR_UNROLL_EFAC
-#define STN_PAIR_UNROLL_EFAC 2         /* same, EFAC on: measured 50.8 vs 51.7 ms (variant C) */
+#ifndef STN_EFAC_UNROLL
+#define STN_EFAC_UNROLL 2              /* unroll factor of the EFAC epoch loop */
 #endif
-#ifndef STN_QUAD_EFAC
-#define STN_QUAD_EFAC 1                /* EFAC: one reciprocal per four epochs (else per two) */
-#endif
-#ifndef STN_RCP_CUBIC
-#define STN_RCP_CUBIC 1            /* 1: cubic refinement of the reciprocal seed, 0: one Newton step */
+// EFAC: exponent budget (bits) the running product of variances may drift between two
+// renormalisations; the double range is +-1022 and T stays within ~2^70 of Q.
+#ifndef STN_RENORM_BITS
+#define STN_RENORM_BITS 700
 #endif
 
 namespace {
@@ -78,7 +89,7 @@ constexpr int kThreads = 256;      // threads per CTA of the likelihood kernels
 constexpr int kChunk = STN_CHUNK;  // epochs per shared-memory stage (128 * 96 B = 12 KiB)
 constexpr int kStages = 2;
 constexpr int kPairUnroll = STN_PAIR_UNROLL;
-constexpr int kPairUnrollEfac = STN_PAIR_UNROLL_EFAC;
+constexpr int kEfacUnroll = STN_EFAC_UNROLL;
 constexpr int kFirst = 1, kLast = 2;
 
 struct SrcDev {
@@ -88,8 +99,10 @@ struct SrcDev {
     int col[STN_NROOTS];
     int efac_on;
     int binary;
-    int grouped;          // EFAC: 4 variances may be multiplied before an exponent extraction
-    int pad;
+    int v_shift;          // EFAC: the variance columns of fast_rows are stored times 2^v_shift
+    int v_lo_bits;        // EFAC: every (scaled) variance is >= 2^-v_lo_bits
+    double v_hi, v_hib;   // EFAC: every (scaled) variance is <= v_hi + g * v_hib, g = max(g_ra, g_dec)
+    double chi_scale;     // EFAC: 2^v_shift, turns the scaled chi-square back
     double cos_decj;
     double inv_cos_decj;
     double neg_sum_log_err;
@@ -155,6 +168,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // fill one stage with `n_epochs` rows (an empty chunk just completes the phase)
 __device__ __forceinline__ void stage_fill(double* dst, const double* src, int n_epochs, uint64_t* bar) {
     const uint32_t bytes = (uint32_t)n_epochs * STN_FAST_ROW * (uint32_t)sizeof(double);
+    STN_ASSERT(n_epochs >= 0 && n_epochs <= kChunk);
     if (bytes != 0) {
         mbar_expect_tx(bar, bytes);
         bulk_g2s(dst, src, bytes, bar);
@@ -182,6 +196,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ double load_param(const double* __restrict__ theta, int64_t n, int col,
                                              int64_t ld, int layout) {
     if (col < 0) return STN_SENTINEL;
+    STN_ASSERT(n >= 0 && (layout == STN_LAYOUT_SOA ? n < ld : col < ld));
     return layout == STN_LAYOUT_SOA ? __ldg(theta + (int64_t)col * ld + n)
                                     : __ldg(theta + n * ld + col);
 }
@@ -284,31 +299,16 @@ __device__ __forceinline__ void fast_offsets(const Coef& c, const double2 tx, co
     }
 }
 
-// 1/v for positive normal v: MUFU.RCP64H seed + one cubic step (relative error ~1e-16).
-__device__ __forceinline__ double fast_rcp(double v) {
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(v));
-    const double e = fma(-v, y, 1.0);
-#if STN_RCP_CUBIC
-    const double p = fma(e, e, e);
-    return fma(y, p, y);
-#else
-    return fma(y, e, y);
-#endif
-}
-
-// Split a positive normal double into its mantissa in [1,2) and add its BIASED exponent
-// field to esum (one LEA.HI); the bias is removed once per source, 1023 * (number of splits).
-__device__ __forceinline__ double split_exp(double v, int& esum) {
-    const int hi = __double2hiint(v);
-    esum += hi >> 20;
-    return __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(v));
-}
-
+// EFAC accumulators of one (sample, source).  The chi-square sum  sum_i s_i / p_i  (one term per
+// epoch, p_i = v_ra v_dec, s_i = r_ra^2 v_dec + r_dec^2 v_ra) is carried as ONE running fraction
+// T / Q with  T <- T p_i + s_i Q,  Q <- Q p_i : no reciprocal in the epoch loop at all, and Q is at
+// the same time the product of all variances, i.e. the log-determinant (sum ln sigma = 1/2 ln Q).
+// Both are kept in range by multiplying T and Q with the same power of two every few epochs
+// (renorm); that scaling is exact, so how often it happens never changes a result bit.
 struct Acc {
-    double chi_ra, chi_dec;   // sum of (res/sigma)^2 per coordinate
-    double prod;              // EFAC: running product of variances, renormalised into [1,2)
-    int esum;                 // EFAC: running sum of biased exponents taken out of prod
+    double chi_ra, chi_dec;   // EFAC off: sum of (res/sigma)^2 per coordinate.  EFAC on: chi_ra = T
+    double prod;              // EFAC on: Q
+    int esum;                 // EFAC on: exponents taken out of Q so far (unbiased)
 };
 
 // Residuals of one epoch of one sample, and for EFAC sources the two variances.
@@ -316,6 +316,7 @@ template <bool EF, bool BIN>
 __device__ __forceinline__ void epoch_residuals(const double* __restrict__ rows, int e, const Coef& cf,
                                                 double& res_ra, double& res_dec, double& v_ra, double& v_dec,
                                                 double2& aa) {
+    STN_ASSERT(e >= 0 && e < kChunk);
     const double2* row = reinterpret_cast<const double2*>(rows + e * STN_FAST_ROW);
     const double2 tx = row[0];
     const double2 yz = row[1];
@@ -331,16 +332,13 @@ __device__ __forceinline__ void epoch_residuals(const double* __restrict__ rows,
     res_dec = ob.y - (cf.dec + odec);
     if (EF) {
         const double2 bb = row[4];
-        v_ra = fma(cf.g_ra, bb.x, aa.x);                  // simulate.py:317
+        v_ra = fma(cf.g_ra, bb.x, aa.x);                  // simulate.py:317 (table pre-scaled by 2^k)
         v_dec = fma(cf.g_dec, bb.y, aa.y);
     }
 }
 
-// One epoch of one sample.  EFAC: r_a^2/v_a + r_d^2/v_d = (r_a^2 v_d + r_d^2 v_a) / (v_a v_d) costs one
-// reciprocal, and the product p = v_a v_d is also the epoch's factor of the log-determinant.
-// SPLIT_EACH (tables whose variances could leave the double range when multiplied): one reciprocal
-// and one exponent extraction per variance.
-template <bool EF, bool BIN, bool SPLIT_EACH>
+// One epoch of one sample.
+template <bool EF, bool BIN>
 __device__ __forceinline__ void epoch_term(const double* __restrict__ rows, int e, const Coef& cf, Acc& acc) {
     double res_ra, res_dec, v_ra = 1.0, v_dec = 1.0;
     double2 aa;
@@ -350,114 +348,73 @@ __device__ __forceinline__ void epoch_term(const double* __restrict__ rows, int 
         const double z_dec = res_dec * aa.y;
         acc.chi_ra = fma(z_ra, z_ra, acc.chi_ra);
         acc.chi_dec = fma(z_dec, z_dec, acc.chi_dec);
-    } else if (SPLIT_EACH) {
-        acc.chi_ra = fma(res_ra * res_ra, fast_rcp(v_ra), acc.chi_ra);
-        acc.chi_dec = fma(res_dec * res_dec, fast_rcp(v_dec), acc.chi_dec);
-        acc.prod = split_exp(acc.prod * v_ra, acc.esum);
-        acc.prod = split_exp(acc.prod * v_dec, acc.esum);
     } else {
         const double p = v_ra * v_dec;
         double s = (res_ra * res_ra) * v_dec;
         s = fma(res_dec * res_dec, v_ra, s);
-        acc.chi_ra = fma(s, fast_rcp(p), acc.chi_ra);
-        acc.prod = split_exp(acc.prod * p, acc.esum);
+        const double sq = s * acc.prod;
+        acc.chi_ra = fma(acc.chi_ra, p, sq);              // T <- T p + s Q   (one FMA on the T chain)
+        acc.prod = acc.prod * p;                          // Q <- Q p
     }
 }
 
-// (s, p) of one EFAC epoch: s = r_ra^2 v_dec + r_dec^2 v_ra, p = v_ra v_dec, so that the epoch's
-// chi-square contribution is s / p and its log-determinant factor is p.
-template <bool BIN>
-__device__ __forceinline__ void epoch_sp(const double* __restrict__ rows, int e, const Coef& cf, double& s,
-                                         double& p) {
-    double res_ra, res_dec, v_ra, v_dec;
-    double2 aa;
-    epoch_residuals<true, BIN>(rows, e, cf, res_ra, res_dec, v_ra, v_dec, aa);
-    p = v_ra * v_dec;
-    s = (res_ra * res_ra) * v_dec;
-    s = fma(res_dec * res_dec, v_ra, s);
+// Take the exponent out of Q and apply the same power of two to T (exact).
+__device__ __forceinline__ void renorm(Acc& acc) {
+    const int hi = __double2hiint(acc.prod);
+    const int ex = (hi >> 20) & 0x7ff;                    // biased exponent of Q (> 0: Q is a positive normal)
+    acc.esum += ex - 1023;
+    acc.prod = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(acc.prod));
+    acc.chi_ra *= __hiloint2double((2046 - ex) << 20, 0); // 2^(1023 - ex)
 }
 
-// Two epochs of one EFAC sample with ONE reciprocal for all four variances:
-//   s_a/p_a + s_b/p_b = (s_a p_b + s_b p_a) / (p_a p_b)
-// and p_a p_b is the pair's factor of the log-determinant.  (t, q) = (numerator, denominator).
-template <bool BIN>
-__device__ __forceinline__ void epoch_pair_tq(const double* __restrict__ rows, int ea, int eb, const Coef& cf,
-                                              double& t, double& q) {
-    double s_a, p_a, s_b, p_b;
-    epoch_sp<BIN>(rows, ea, cf, s_a, p_a);
-    epoch_sp<BIN>(rows, eb, cf, s_b, p_b);
-    q = p_a * p_b;
-    t = s_a * p_b;
-    t = fma(s_b, p_a, t);
-}
-
-template <bool BIN>
-__device__ __forceinline__ void epoch_pair_efac(const double* __restrict__ rows, int ea, int eb, const Coef& cf,
-                                                Acc& acc) {
-    double t, q;
-    epoch_pair_tq<BIN>(rows, ea, eb, cf, t, q);
-    acc.chi_ra = fma(t, fast_rcp(q), acc.chi_ra);
-    acc.prod = split_exp(acc.prod * q, acc.esum);
-}
-
-// Four epochs, eight variances, one reciprocal and one exponent extraction.
-template <bool BIN>
-__device__ __forceinline__ void epoch_quad_efac(const double* __restrict__ rows, int e, int step, const Coef& cf,
-                                                Acc& acc) {
-    double t1, q1, t2, q2;
-    epoch_pair_tq<BIN>(rows, e, e + step, cf, t1, q1);
-    epoch_pair_tq<BIN>(rows, e + 2 * step, e + 3 * step, cf, t2, q2);
-    const double q = q1 * q2;
-    double t = t1 * q2;
-    t = fma(t2, q1, t);
-    acc.chi_ra = fma(t, fast_rcp(q), acc.chi_ra);
-    acc.prod = split_exp(acc.prod * q, acc.esum);
-}
-
-// Returns the number of exponent extractions made per sample (the same for every sample of
-// the thread).  !SPLIT_EACH: one extraction per four epochs (eight variances), then per pair and
-// per single epoch for the remainder; the host enables it only when eight variances cannot
-// overflow / underflow (see stn_create).
-template <int R, int L, bool QUAD, bool EF, bool BIN, bool SPLIT_EACH>
-__device__ __forceinline__ int epoch_loop(const double* __restrict__ rows, int n_epochs, int sub,
-                                          const Coef (&cf)[R], Acc (&acc)[R]) {
+// Epochs sub, sub + L, ... of one staged chunk for the R samples of this thread.  `mask` + 1 is the
+// (warp-uniform) number of epochs between two renormalisations of the EFAC accumulators.
+template <int R, int L, bool EF, bool BIN>
+__device__ __forceinline__ void epoch_loop(const double* __restrict__ rows, int n_epochs, int sub,
+                                           const Coef (&cf)[R], Acc (&acc)[R], int mask) {
     int e = sub;
-    // QUAD is a property of the PROBLEM (EFAC-heavy or not), never of the batch size: the grouping
-    // of the reciprocal changes rounding, and a sample's bits must not depend on R or on sharding
-    constexpr bool kQuad = EF && !SPLIT_EACH && QUAD;
-    if (kQuad) {
-#pragma unroll 1
-        for (; e + 3 * L < n_epochs; e += 4 * L) {
+    if constexpr (EF) {
+        while (e < n_epochs) {
+            const int span = (mask + 1) * L;
+            const int stop = (n_epochs - e > span) ? e + span : n_epochs;
+#pragma unroll kEfacUnroll
+            for (; e < stop; e += L) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) epoch_quad_efac<BIN>(rows, e, L, cf[r], acc[r]);
+                for (int r = 0; r < R; ++r) epoch_term<true, BIN>(rows, e, cf[r], acc[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) renorm(acc[r]);
         }
-    }
-    // the deeper unroll only pays in the R = 3 kernel (EFAC problems); in the 128-register R <= 2
-    // kernels it costs spills that also slow their non-EFAC loops
-    constexpr int kUnroll = (EF && !SPLIT_EACH && R >= 3 && !kQuad) ? kPairUnrollEfac : kPairUnroll;
-#pragma unroll kUnroll
-    for (; e + L < n_epochs; e += 2 * L) {
+    } else {
+#pragma unroll kPairUnroll
+        for (; e + L < n_epochs; e += 2 * L) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if (EF && !SPLIT_EACH) {
-                epoch_pair_efac<BIN>(rows, e, e + L, cf[r], acc[r]);
-            } else {
-                epoch_term<EF, BIN, SPLIT_EACH>(rows, e, cf[r], acc[r]);
-                epoch_term<EF, BIN, SPLIT_EACH>(rows, e + L, cf[r], acc[r]);
+            for (int r = 0; r < R; ++r) {
+                epoch_term<false, BIN>(rows, e, cf[r], acc[r]);
+                epoch_term<false, BIN>(rows, e + L, cf[r], acc[r]);
             }
         }
-    }
-    if (e < n_epochs) {
+        if (e < n_epochs) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) epoch_term<EF, BIN, SPLIT_EACH>(rows, e, cf[r], acc[r]);
+            for (int r = 0; r < R; ++r) epoch_term<false, BIN>(rows, e, cf[r], acc[r]);
+        }
     }
-    // epochs handled by this lane: sub, sub+L, ...
-    const int cnt = sub < n_epochs ? (n_epochs - sub + L - 1) / L : 0;
-    if (!EF) return 0;
-    if (SPLIT_EACH) return 2 * cnt;
-    const int quads = kQuad ? cnt / 4 : 0;
-    const int rem = cnt - 4 * quads;
-    return quads + (rem + 1) / 2;
+}
+
+// Epochs between two renormalisations for this sample: the largest power of two (minus one, as a
+// mask) such that the product of that many epochs' variance pairs stays within STN_RENORM_BITS
+// binary orders of magnitude.  Any variance of the source lies in [v_lo, v_hi + g v_hib].
+__device__ __forceinline__ int renorm_mask(const SrcDev& S, const Coef& c) {
+    const double g = fmax(c.g_ra, c.g_dec);
+    const double vmax = fma(g, S.v_hib, S.v_hi);
+    const int ex = ((__double2hiint(vmax) >> 20) & 0x7ff) - 1023;          // inf / nan -> 1024
+    const int up = ex >= 0 ? ex + 1 : 0;
+    const int bits = 2 * (up > S.v_lo_bits ? up : S.v_lo_bits);            // one epoch = two variances
+    if (bits <= 0) return kChunk - 1;
+    int m = STN_RENORM_BITS / bits;
+    if (m < 1) m = 1;
+    if (m > kChunk) m = kChunk;
+    return (1 << (31 - __clz(m))) - 1;
 }
 
 template <int L>
@@ -532,7 +489,7 @@ __device__ double prior_terms(const ProbDev& P, const double* __restrict__ theta
 __host__ __device__ constexpr int threads_for(int R) { return R > 2 ? STN_THREADS_R3 : (R == 2 ? STN_THREADS_R2 : kThreads); }
 __host__ __device__ constexpr int minblocks_for(int R) { return R > 2 ? STN_MINBLOCKS_R3 : (R == 2 ? STN_MINBLOCKS_R2 : 2); }
 
-template <int R, int L, bool QUAD>
+template <int R, int L>
 __global__ void __launch_bounds__(threads_for(R), minblocks_for(R))
 stn_loglike_fast_kernel(const ProbDev P, const double* __restrict__ theta, const int64_t N,
                         const int64_t ld, const int layout, double* __restrict__ out,
@@ -553,6 +510,7 @@ stn_loglike_fast_kernel(const ProbDev P, const double* __restrict__ theta, const
         const int64_t n = tile_base + (int64_t)r * G + grp;
         valid[r] = n < N;
         nidx[r] = valid[r] ? n : (N - 1);
+        STN_ASSERT(nidx[r] >= 0 && nidx[r] < N);
     }
 
     if (tid == 0) {
@@ -574,12 +532,18 @@ stn_loglike_fast_kernel(const ProbDev P, const double* __restrict__ theta, const
     double logl[R];
     Coef cf[R];
     Acc acc[R];
-    int nsplit = 0;
+    int mask = kChunk - 1;        // EFAC: epochs between two renormalisations, minus one (warp-uniform)
+    int nvar = 0;                 // EFAC: epochs this lane has folded into Q since `first`
 #pragma unroll
     for (int r = 0; r < R; ++r) logl[r] = 0.0;
 
     for (int c = c_begin; c < c_end; ++c) {
+        STN_ASSERT(c >= 0 && c < P.n_chunks);
         const ChunkDev ck = P.chunks[c];
+        STN_ASSERT(ck.source >= 0 && ck.source < P.n_sources && ck.n_epochs <= kChunk);
+        STN_ASSERT(ck.rows >= P.src[ck.source].fast_rows &&
+                   ck.rows + (size_t)ck.n_epochs * STN_FAST_ROW <=
+                       P.src[ck.source].fast_rows + (size_t)P.src[ck.source].n_epochs * STN_FAST_ROW);
         const int it = c - c_begin;                      // stage = it & 1, phase parity = (it >> 1) & 1
         if (tid == 0 && c + 1 < c_end) {
             // stage (it+1)&1 was last read in iteration it-1; the __syncthreads that ended it
@@ -590,7 +554,10 @@ stn_loglike_fast_kernel(const ProbDev P, const double* __restrict__ theta, const
         const SrcDev& S = P.src[ck.source];
         const bool first = (ck.flags & kFirst) || c == c_begin;   // (re)start this source's sums
         const bool last = (ck.flags & kLast) || c == c_end - 1;   // fold them into log L
+        const bool ef = S.efac_on != 0;
+        const bool bin = S.binary != 0;
         if (first) {
+            int m = kChunk - 1;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const Params p = load_params(S, theta, nidx[r], ld, layout);
@@ -599,32 +566,35 @@ stn_loglike_fast_kernel(const ProbDev P, const double* __restrict__ theta, const
                 acc[r].chi_dec = 0.0;
                 acc[r].prod = 1.0;
                 acc[r].esum = 0;
+                if (ef) m = min(m, renorm_mask(S, cf[r]));
             }
+            // the cadence only has to be uniform over the warp (the epoch loops stay converged); it
+            // never changes a bit of the result
+            mask = ef ? __reduce_min_sync(0xffffffffu, m) : m;
+            nvar = 0;
         }
         mbar_wait(&full[it & 1], (uint32_t)((it >> 1) & 1));
         const double* rows = stage[it & 1];
-        const bool ef = S.efac_on != 0;
-        const bool bin = S.binary != 0;
-        const bool grouped = S.grouped != 0;
-        if (first) nsplit = 0;
-        if (!ef && !bin) epoch_loop<R, L, QUAD, false, false, false>(rows, ck.n_epochs, sub, cf, acc);
-        else if (!ef && bin) epoch_loop<R, L, QUAD, false, true, false>(rows, ck.n_epochs, sub, cf, acc);
-        else if (ef && !bin && grouped) nsplit += epoch_loop<R, L, QUAD, true, false, false>(rows, ck.n_epochs, sub, cf, acc);
-        else if (ef && bin && grouped) nsplit += epoch_loop<R, L, QUAD, true, true, false>(rows, ck.n_epochs, sub, cf, acc);
-        else if (ef && !bin) nsplit += epoch_loop<R, L, QUAD, true, false, true>(rows, ck.n_epochs, sub, cf, acc);
-        else nsplit += epoch_loop<R, L, QUAD, true, true, true>(rows, ck.n_epochs, sub, cf, acc);
+        if (!ef && !bin) epoch_loop<R, L, false, false>(rows, ck.n_epochs, sub, cf, acc, mask);
+        else if (!ef && bin) epoch_loop<R, L, false, true>(rows, ck.n_epochs, sub, cf, acc, mask);
+        else if (ef && !bin) epoch_loop<R, L, true, false>(rows, ck.n_epochs, sub, cf, acc, mask);
+        else epoch_loop<R, L, true, true>(rows, ck.n_epochs, sub, cf, acc, mask);
+        if (ef) nvar += sub < ck.n_epochs ? (ck.n_epochs - sub + L - 1) / L : 0;
 
         if (last) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 // log_p += -0.5*sum((res/errs)^2); log_p += -sum(log(errs))  (simulate.py:370-371)
-                const double chi = group_sum<L>(acc[r].chi_ra + acc[r].chi_dec);
-                double logdet;
+                double chi, logdet;
                 if (ef) {
-                    // -sum(log sigma) = -0.5 * log(prod of variances)
-                    const double part = log(acc[r].prod) + (double)(acc[r].esum - 1023 * nsplit) * STN_LN2;
+                    // chi^2 = 2^k T / Q;  -sum(log sigma) = -0.5 log(prod of variances), the table's
+                    // variances being stored times 2^k (two per epoch)
+                    renorm(acc[r]);                                   // Q into [1, 2): log() sees the same bits
+                    chi = group_sum<L>((acc[r].chi_ra / acc[r].prod) * S.chi_scale);
+                    const double part = log(acc[r].prod) + (double)(acc[r].esum - 2 * nvar * S.v_shift) * STN_LN2;
                     logdet = -0.5 * group_sum<L>(part);
                 } else {
+                    chi = group_sum<L>(acc[r].chi_ra + acc[r].chi_dec);
                     // host constant, counted once: by the split that holds the source's last chunk
                     logdet = (ck.flags & kLast) ? S.neg_sum_log_err : 0.0;
                 }
@@ -642,7 +612,10 @@ stn_loglike_fast_kernel(const ProbDev P, const double* __restrict__ theta, const
     if (K > 1) {
 #pragma unroll
         for (int r = 0; r < R; ++r)
-            if (valid[r] && sub == 0) partial[(int64_t)blockIdx.y * N + nidx[r]] = logl[r];
+            if (valid[r] && sub == 0) {
+                STN_ASSERT(partial != nullptr && blockIdx.y < gridDim.y);
+                partial[(int64_t)blockIdx.y * N + nidx[r]] = logl[r];
+            }
         return;
     }
 #pragma unroll
@@ -758,10 +731,8 @@ stn_loglike_strict_kernel(const ProbDev P, const double* __restrict__ theta, con
                         const double v = __dadd_rn(__dmul_rn(row[8 + half], row[8 + half]), __dmul_rn(q, q));
                         err = __dsqrt_rn(v);
                     } else {
-                        // efac sampled as exactly -999: errs^2 ~ err_random^2 + err_sys^2
-                        const double v = __dadd_rn(__dmul_rn(row[8 + half], row[8 + half]),
-                                                   __dmul_rn(row[10 + half], row[10 + half]));
-                        err = __dsqrt_rn(v);
+                        // efac sampled as exactly -999: errs_new = (errs**2)**0.5 = errs   (simulate.py:318-320)
+                        err = row[6 + half];
                     }
                     slog = __dadd_rn(slog, log(err));
                 } else {
@@ -799,6 +770,7 @@ stn_model_kernel(const ProbDev P, const int source, const double* __restrict__ t
     if (idx >= N * E) return;
     const int64_t n = idx / E;
     const int e = (int)(idx - n * E);
+    STN_ASSERT(n >= 0 && n < N && e >= 0 && e < E);
     const Params p = load_params(S, theta, n, ld, layout);
     double m_ra, m_dec, o_ra, o_dec;
     if (mode == STN_MODE_STRICT) {
@@ -955,15 +927,29 @@ struct StnCtx {
     // zero-copy staging for small host batches (pinned, mapped: the kernel reads / writes it directly)
     double* small_in = nullptr;
     double* small_out = nullptr;
-    double* scratch[3] = {nullptr, nullptr, nullptr};   // split partial sums: [0] device API, [1],[2] host streams
-    int64_t scratch_elems[3] = {0, 0, 0};
+    static constexpr int kSlots = 3;    // host pipeline depth: H2D of chunk i+1, kernel of chunk i, D2H of chunk i-1
+    double* scratch[1 + kSlots] = {};   // split partial sums: [0] device API, [1 + slot] host pipeline
+    int64_t scratch_elems[1 + kSlots] = {};
     int64_t launches = 0;
-    // *_host staging
-    cudaStream_t streams[2] = {nullptr, nullptr};
-    cudaStream_t timing_stream = nullptr;
-    double* stage_theta[2] = {nullptr, nullptr};
-    double* stage_out[2] = {nullptr, nullptr};
+    // *_host pipeline: one stream, one device staging pair and (for pageable caller buffers) one pinned
+    // staging pair per slot
+    cudaStream_t streams[kSlots] = {};
+    cudaEvent_t h2d_done[kSlots] = {};
+    cudaEvent_t d2h_done[kSlots] = {};
+    double* stage_theta[kSlots] = {};
+    double* stage_out[kSlots] = {};
     int64_t stage_rows = 0;
+    double* pin_theta[kSlots] = {};
+    double* pin_out[kSlots] = {};
+    int64_t pin_rows = 0;
+    cudaStream_t timing_stream = nullptr;
+    double* gather_buf = nullptr;       // stn_multi_loglike_dev: this device's slice before the peer copy
+    int64_t gather_elems = 0;
+};
+
+// Several contexts of the same problem, one per device, driven as one (stn_multi_*).
+struct StnMulti {
+    std::vector<StnCtx*> ctx;
 };
 
 namespace {
@@ -978,6 +964,29 @@ int upload(StnCtx* ctx, const T* host, size_t count, const T** dev_out) {
     *dev_out = static_cast<const T*>(d);
     return STN_OK;
 }
+
+#ifdef STN_DEBUG
+// the `bytes` starting at device pointer p must lie inside one allocation known to the driver
+int dbg_range(const void* p, size_t bytes, const char* what) {
+    if (bytes == 0) return STN_OK;
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    const CUresult r = cuMemGetAddressRange(&base, &size, (CUdeviceptr)(uintptr_t)p);
+    if (r != CUDA_SUCCESS) return fail(STN_ERR_INVALID, "STN_DEBUG: %s (%p) is not inside a CUDA allocation", what, p);
+    const uintptr_t lo = (uintptr_t)p, hi = lo + bytes;
+    if (lo < (uintptr_t)base || hi > (uintptr_t)base + size)
+        return fail(STN_ERR_INVALID, "STN_DEBUG: %s needs %zu bytes at %p but its allocation is [%p, +%zu)", what, bytes,
+                    p, (void*)(uintptr_t)base, size);
+    return STN_OK;
+}
+size_t dbg_theta_bytes(int64_t n, int64_t ld, int layout, int P) {
+    if (n == 0) return 0;
+    return sizeof(double) * (size_t)(layout == STN_LAYOUT_AOS ? (n - 1) * ld + P : (int64_t)(P - 1) * ld + n);
+}
+#define STN_DBG_RANGE(p, bytes, what) do { const int r_ = dbg_range(p, bytes, what); if (r_) return r_; } while (0)
+#else
+#define STN_DBG_RANGE(p, bytes, what) ((void)0)
+#endif
 
 // ---- execution plan -------------------------------------------------------------------
 // plan = lanes | (splits << 8).  lanes: lanes of a warp sharing one sample (epochs of a chunk
@@ -1040,7 +1049,7 @@ int pick_plan(const StnCtx* ctx, int64_t n) {
     return make_plan(L, K);
 }
 
-template <int R, int L, bool QUAD>
+template <int R, int L>
 int launch_fast(StnCtx* ctx, const ProbDev& prob, const double* theta, int64_t n, int64_t ld, int layout,
                 double* out, cudaStream_t st, int splits, double* partial) {
     constexpr int per_cta = (threads_for(R) / L) * R;
@@ -1048,7 +1057,7 @@ int launch_fast(StnCtx* ctx, const ProbDev& prob, const double* theta, int64_t n
     if (grid > 0x7fffffffLL) return fail(STN_ERR_INVALID, "batch too large for one launch");
     dim3 g((unsigned)grid, (unsigned)splits, 1);
     (void)cudaGetLastError();      // other CUDA users of this process (torch) may have left a stale error
-    stn_loglike_fast_kernel<R, L, QUAD><<<g, threads_for(R), 0, st>>>(prob, theta, n, ld, layout, out, partial);
+    stn_loglike_fast_kernel<R, L><<<g, threads_for(R), 0, st>>>(prob, theta, n, ld, layout, out, partial);
     STN_CUDA(cudaGetLastError());
     ctx->launches++;
     if (splits > 1) {
@@ -1060,7 +1069,7 @@ int launch_fast(StnCtx* ctx, const ProbDev& prob, const double* theta, int64_t n
     return STN_OK;
 }
 
-// scratch_slot: 0 for the device-buffer API, 1/2 for the two streams of the host API
+// scratch_slot: 0 for the device-buffer API, 1 + slot for the streams of the host pipeline
 int launch_loglike(StnCtx* ctx, const double* theta, int64_t n, int64_t ld, int layout, int mode,
                    int plan, double* out, cudaStream_t st, int what = 0, int scratch_slot = 0) {
     // what: 0 = log L, 1 = log prior + log L, 2 = chi-square
@@ -1068,6 +1077,8 @@ int launch_loglike(StnCtx* ctx, const double* theta, int64_t n, int64_t ld, int 
     ProbDev prob = what == 1 ? ctx->prior_prob : ctx->prob;
     prob.out_chisq = what == 2 ? 1 : 0;
     if (mode == STN_MODE_STRICT) {
+        STN_DBG_RANGE(theta, dbg_theta_bytes(n, ld, layout, ctx->prob.n_params), "theta");
+        STN_DBG_RANGE(out, (size_t)n * sizeof(double), "out");
         const int64_t grid = (n + kThreads - 1) / kThreads;
         (void)cudaGetLastError();
         stn_loglike_strict_kernel<<<(unsigned)grid, kThreads, 0, st>>>(prob, theta, n, ld, layout, out);
@@ -1088,7 +1099,9 @@ int launch_loglike(StnCtx* ctx, const double* theta, int64_t n, int64_t ld, int 
         const int64_t need = (int64_t)splits * n;
         if (ctx->scratch_elems[scratch_slot] < need) {
             if (ctx->scratch[scratch_slot]) {
-                STN_CUDA(cudaStreamSynchronize(st));
+                // slot 0 may have been used from another of the caller's streams before
+                if (scratch_slot == 0) STN_CUDA(cudaDeviceSynchronize());
+                else STN_CUDA(cudaStreamSynchronize(st));
                 STN_CUDA(cudaFree(ctx->scratch[scratch_slot]));
                 ctx->scratch[scratch_slot] = nullptr;
                 ctx->scratch_elems[scratch_slot] = 0;
@@ -1098,20 +1111,17 @@ int launch_loglike(StnCtx* ctx, const double* theta, int64_t n, int64_t ld, int 
         }
         partial = ctx->scratch[scratch_slot];
     }
+    STN_DBG_RANGE(theta, dbg_theta_bytes(n, ld, layout, ctx->prob.n_params), "theta");
+    STN_DBG_RANGE(out, (size_t)n * sizeof(double), "out");
+    if (partial) STN_DBG_RANGE(partial, (size_t)splits * n * sizeof(double), "split scratch");
     const int R = choose_R(ctx, n, lanes, splits);
-    // EFAC-heavy problems: big kernel R = STN_RBIG_EFAC, reciprocal shared by four epochs (QUAD);
-    // other problems: big kernel R = STN_RBIG, reciprocal shared by two epochs
-    const bool quad = ctx->efac_heavy && STN_QUAD_EFAC;
-#define STN_GO(RR, LL)                                                                                          \
-    do {                                                                                                        \
-        if (quad) return launch_fast<RR, LL, true>(ctx, prob, theta, n, ld, layout, out, st, splits, partial);  \
-        return launch_fast<RR, LL, false>(ctx, prob, theta, n, ld, layout, out, st, splits, partial);           \
-    } while (0)
+    // EFAC-heavy problems use the R = STN_RBIG_EFAC kernel for large batches, others R = STN_RBIG
+#define STN_GO(RR, LL) return launch_fast<RR, LL>(ctx, prob, theta, n, ld, layout, out, st, splits, partial)
     switch (lanes) {
         case 1:
             if (R > 1) {
-                if (quad) return launch_fast<STN_RBIG_EFAC, 1, true>(ctx, prob, theta, n, ld, layout, out, st, splits, partial);
-                return launch_fast<STN_RBIG, 1, false>(ctx, prob, theta, n, ld, layout, out, st, splits, partial);
+                if (ctx->efac_heavy) STN_GO(STN_RBIG_EFAC, 1);
+                STN_GO(STN_RBIG, 1);
             }
             STN_GO(1, 1);
         case 2: STN_GO(1, 2);
@@ -1136,6 +1146,177 @@ int check_call(StnCtx* ctx, const void* theta, int64_t n, int64_t ld, int layout
     if (layout == STN_LAYOUT_SOA && ld < n)
         return fail(STN_ERR_INVALID, "SoA leading dimension %lld < n = %lld", (long long)ld, (long long)n);
     return STN_OK;
+}
+
+
+// ---- host-buffer pipeline ---------------------------------------------------------------
+// true when the CUDA runtime knows `p` as pinned (page-locked) host memory, i.e. a DMA target
+bool is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
+int host_pipe_init(StnCtx* ctx) {
+    for (int i = 0; i < StnCtx::kSlots; ++i) {
+        if (!ctx->streams[i]) STN_CUDA(cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking));
+        if (!ctx->h2d_done[i]) STN_CUDA(cudaEventCreateWithFlags(&ctx->h2d_done[i], cudaEventDisableTiming));
+        if (!ctx->d2h_done[i]) STN_CUDA(cudaEventCreateWithFlags(&ctx->d2h_done[i], cudaEventDisableTiming));
+    }
+    return STN_OK;
+}
+
+void host_pipe_drain(StnCtx* ctx) {
+    for (int i = 0; i < StnCtx::kSlots; ++i)
+        if (ctx->streams[i]) cudaStreamSynchronize(ctx->streams[i]);
+}
+
+// Rows of the k-th chunk: a short first chunk (its H2D copy is the only one nothing overlaps),
+// doubling up to 2^18 rows.
+constexpr int64_t kChunkRowsMax = (int64_t)1 << 18;
+int64_t first_chunk_rows(int64_t n) {
+    int64_t r = n / 32;
+    if (r > ((int64_t)1 << 15)) r = (int64_t)1 << 15;
+    if (r < 4096) r = 4096;
+    return r < n ? r : n;
+}
+
+// One slice of a host batch on this context's device: H2D, kernel(s), D2H, synchronised on return.
+// The caller has made ctx->device current and resolved `plan` from the WHOLE batch.
+int run_host(StnCtx* ctx, const double* theta_host, int64_t n, int64_t ld, int layout, int mode, int plan,
+             double* out_host) {
+    const int P = ctx->prob.n_params;
+    int rc = host_pipe_init(ctx);
+    if (rc) return rc;
+    // Small batches (a sampler evaluating one point, or a few walkers) are latency-bound: skip both
+    // cudaMemcpy calls by letting the kernel read the parameters from, and write log L to, pinned
+    // mapped host memory.  One launch + one stream synchronise.
+    constexpr int64_t kSmallBytes = 64 * 1024, kSmallRows = 2048;
+    if (layout == STN_LAYOUT_AOS && n <= kSmallRows && n * P * (int64_t)sizeof(double) <= kSmallBytes) {
+        if (!ctx->small_in) STN_CUDA(cudaHostAlloc((void**)&ctx->small_in, kSmallBytes, cudaHostAllocMapped));
+        if (!ctx->small_out) STN_CUDA(cudaHostAlloc((void**)&ctx->small_out, kSmallRows * sizeof(double), cudaHostAllocMapped));
+        for (int64_t i = 0; i < n; ++i) std::memcpy(ctx->small_in + i * P, theta_host + i * ld, (size_t)P * sizeof(double));
+        rc = launch_loglike(ctx, ctx->small_in, n, P, layout, mode, plan, ctx->small_out, ctx->streams[0], 0, 1);
+        const cudaError_t e = cudaStreamSynchronize(ctx->streams[0]);
+        if (rc) return rc;
+        if (e != cudaSuccess) return fail(STN_ERR_CUDA, "small-batch launch failed: %s", cudaGetErrorString(e));
+        std::memcpy(out_host, ctx->small_out, (size_t)n * sizeof(double));
+        return STN_OK;
+    }
+    const bool pin_in = is_pinned(theta_host);
+    const bool pin_out = is_pinned(out_host);
+    const int64_t cap = n < kChunkRowsMax ? n : kChunkRowsMax;
+    // device staging (and, for pageable caller buffers, the library's own pinned ring)
+    if (ctx->stage_rows < cap) {
+        host_pipe_drain(ctx);
+        for (int i = 0; i < StnCtx::kSlots; ++i) {
+            if (ctx->stage_theta[i]) cudaFree(ctx->stage_theta[i]);
+            if (ctx->stage_out[i]) cudaFree(ctx->stage_out[i]);
+            ctx->stage_theta[i] = ctx->stage_out[i] = nullptr;
+        }
+        ctx->stage_rows = 0;
+        for (int i = 0; i < StnCtx::kSlots; ++i) {
+            STN_CUDA(cudaMalloc(&ctx->stage_theta[i], (size_t)cap * P * sizeof(double)));
+            STN_CUDA(cudaMalloc(&ctx->stage_out[i], (size_t)cap * sizeof(double)));
+        }
+        ctx->stage_rows = cap;
+    }
+    if ((!pin_in || !pin_out) && ctx->pin_rows < cap) {
+        host_pipe_drain(ctx);
+        for (int i = 0; i < StnCtx::kSlots; ++i) {
+            if (ctx->pin_theta[i]) cudaFreeHost(ctx->pin_theta[i]);
+            if (ctx->pin_out[i]) cudaFreeHost(ctx->pin_out[i]);
+            ctx->pin_theta[i] = ctx->pin_out[i] = nullptr;
+        }
+        ctx->pin_rows = 0;
+        for (int i = 0; i < StnCtx::kSlots; ++i) {
+            STN_CUDA(cudaHostAlloc((void**)&ctx->pin_theta[i], (size_t)cap * P * sizeof(double), cudaHostAllocDefault));
+            STN_CUDA(cudaHostAlloc((void**)&ctx->pin_out[i], (size_t)cap * sizeof(double), cudaHostAllocDefault));
+        }
+        ctx->pin_rows = cap;
+    }
+
+    struct Pending { int64_t lo, m; bool live; } pend[StnCtx::kSlots] = {};
+    auto body = [&]() -> int {
+        int64_t rows = first_chunk_rows(n);
+        int k = 0;
+        for (int64_t lo = 0; lo < n; ++k) {
+            const int64_t m = (n - lo) < rows ? (n - lo) : rows;
+            const int slot = k % StnCtx::kSlots;
+            cudaStream_t st = ctx->streams[slot];
+            double* dth = ctx->stage_theta[slot];
+            double* dout = ctx->stage_out[slot];
+            // pageable output: the chunk that used this slot last is copied out before the slot is reused
+            if (pend[slot].live) {
+                STN_CUDA(cudaEventSynchronize(ctx->d2h_done[slot]));
+                std::memcpy(out_host + pend[slot].lo, ctx->pin_out[slot], (size_t)pend[slot].m * sizeof(double));
+                pend[slot].live = false;
+            }
+            const double* src;
+            int64_t src_ld;                 // leading dimension of the host image that is DMA'd
+            if (pin_in) {
+                src = layout == STN_LAYOUT_AOS ? theta_host + lo * ld : theta_host + lo;
+                src_ld = ld;
+            } else {
+                // pageable input: compact copy into this slot's pinned buffer (the previous DMA out of it is done
+                // once h2d_done has fired), then DMA from there while the next chunk is being copied
+                if (k >= StnCtx::kSlots) STN_CUDA(cudaEventSynchronize(ctx->h2d_done[slot]));
+                double* hp = ctx->pin_theta[slot];
+                if (layout == STN_LAYOUT_AOS) {
+                    if (ld == P) std::memcpy(hp, theta_host + lo * ld, (size_t)m * P * sizeof(double));
+                    else for (int64_t i = 0; i < m; ++i) std::memcpy(hp + i * P, theta_host + (lo + i) * ld, (size_t)P * sizeof(double));
+                    src_ld = P;
+                } else {
+                    for (int c = 0; c < P; ++c) std::memcpy(hp + (int64_t)c * m, theta_host + (int64_t)c * ld + lo, (size_t)m * sizeof(double));
+                    src_ld = m;
+                }
+                src = hp;
+            }
+            int64_t dld;
+            if (layout == STN_LAYOUT_AOS && src_ld == P) {
+                STN_CUDA(cudaMemcpyAsync(dth, src, (size_t)m * P * sizeof(double), cudaMemcpyHostToDevice, st));
+                dld = P;
+            } else if (layout == STN_LAYOUT_AOS) {
+                // padded rows: keep only the first P columns of each
+                STN_CUDA(cudaMemcpy2DAsync(dth, (size_t)P * sizeof(double), src, (size_t)src_ld * sizeof(double),
+                                           (size_t)P * sizeof(double), (size_t)m, cudaMemcpyHostToDevice, st));
+                dld = P;
+            } else {
+                STN_CUDA(cudaMemcpy2DAsync(dth, (size_t)m * sizeof(double), src, (size_t)src_ld * sizeof(double),
+                                           (size_t)m * sizeof(double), (size_t)P, cudaMemcpyHostToDevice, st));
+                dld = m;
+            }
+            if (!pin_in) STN_CUDA(cudaEventRecord(ctx->h2d_done[slot], st));
+            const int r = launch_loglike(ctx, dth, m, dld, layout, mode, plan, dout, st, 0, 1 + slot);
+            if (r) return r;
+            if (pin_out) {
+                STN_CUDA(cudaMemcpyAsync(out_host + lo, dout, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
+            } else {
+                STN_CUDA(cudaMemcpyAsync(ctx->pin_out[slot], dout, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
+                STN_CUDA(cudaEventRecord(ctx->d2h_done[slot], st));
+                pend[slot].lo = lo; pend[slot].m = m; pend[slot].live = true;
+            }
+            lo += m;
+            if (rows < kChunkRowsMax) rows = rows * 2 < kChunkRowsMax ? rows * 2 : kChunkRowsMax;
+        }
+        // the chunks still in flight, oldest first
+        for (int j = 0; j < StnCtx::kSlots; ++j) {
+            const int slot = (k + j) % StnCtx::kSlots;
+            if (pend[slot].live) {
+                STN_CUDA(cudaEventSynchronize(ctx->d2h_done[slot]));
+                std::memcpy(out_host + pend[slot].lo, ctx->pin_out[slot], (size_t)pend[slot].m * sizeof(double));
+                pend[slot].live = false;
+            }
+        }
+        for (int i = 0; i < StnCtx::kSlots; ++i) STN_CUDA(cudaStreamSynchronize(ctx->streams[i]));
+        return STN_OK;
+    };
+    rc = body();
+    if (rc) host_pipe_drain(ctx);     // nothing of this call may still touch the caller's buffers after an error
+    return rc;
 }
 
 }  // namespace
@@ -1194,19 +1375,42 @@ int stn_create(const StnProblem* pb, int device, StnCtx** out_ctx) {
         for (int r = 0; r < STN_NROOTS; ++r) d.col[r] = hs.col[r];
         d.efac_on = hs.efac_on ? 1 : 0;
         d.binary = hs.binary ? 1 : 0;
-        d.grouped = 0;
-        if (d.efac_on) {
-            // variance v = a + g*b with a = err_random^2, b = err_sys^2, g = efac^2 >= 0:
-            // v >= a_min, and v^8 (the product of the eight variances of four epochs) stays inside the
-            // double range for any efac below ~1e11 when the table is within these bounds
-            // (squared radians-scale errors are ~1e-19).
-            double a_min = 1e300, a_max = 0.0, b_max = 0.0;
+        d.v_shift = 0;
+        d.v_lo_bits = 0;
+        d.v_hi = d.v_hib = 0.0;
+        d.chi_scale = 1.0;
+        if (d.efac_on && hs.n_epochs > 0) {
+            // variance v = a + g*b with a = err_random^2, b = err_sys^2, g = efac^2 >= 0 (squared
+            // radian-scale errors, ~1e-19).  The device copy of the four variance columns is stored
+            // times 2^k with k chosen so that the scaled a's straddle 1: products of many variances
+            // then stay in range.  The scaling is exact and undone exactly at the fold.
+            double a_min = INFINITY, a_max = 0.0, b_max = 0.0;
             for (int64_t e = 0; e < hs.n_epochs; ++e) {
                 const double* row = hs.fast_rows + e * STN_FAST_ROW;
                 for (int k = 6; k < 8; ++k) { if (row[k] < a_min) a_min = row[k]; if (row[k] > a_max) a_max = row[k]; }
                 for (int k = 8; k < 10; ++k) if (row[k] > b_max) b_max = row[k];
             }
-            d.grouped = (hs.n_epochs > 0 && a_min >= 1e-30 && a_max <= 1e30 && b_max <= 1e15) ? 1 : 0;
+            const bool usable = std::isfinite(a_max) && std::isfinite(b_max) && a_max > 0.0 && a_min >= 0.0;
+            int k = 0;
+            if (usable) {
+                const double lo = a_min > 0.0 ? a_min : a_max;
+                k = -(std::ilogb(lo) + std::ilogb(a_max)) / 2;
+                if (k > 900) k = 900;
+                if (k < -900) k = -900;
+            }
+            std::vector<double> scaled(hs.fast_rows, hs.fast_rows + (size_t)hs.n_epochs * STN_FAST_ROW);
+            for (int64_t e = 0; e < hs.n_epochs; ++e)
+                for (int c = 6; c < 10; ++c) scaled[(size_t)e * STN_FAST_ROW + c] = std::ldexp(scaled[(size_t)e * STN_FAST_ROW + c], k);
+            if (cudaMemcpy(const_cast<double*>(d.fast_rows), scaled.data(), scaled.size() * sizeof(double),
+                           cudaMemcpyHostToDevice) != cudaSuccess)
+                return bail(fail(STN_ERR_CUDA, "source %d: upload of the scaled variance columns failed", s));
+            d.v_shift = k;
+            d.chi_scale = std::ldexp(1.0, k);
+            d.v_hi = std::ldexp(a_max, k);
+            d.v_hib = std::ldexp(b_max, k);
+            const double lo_s = std::ldexp(a_min, k);
+            // a == 0 somewhere (no random error): nothing bounds the variances from below, renormalise every epoch
+            d.v_lo_bits = (usable && lo_s > 0.0 && std::isfinite(lo_s)) ? (lo_s >= 1.0 ? 0 : -std::ilogb(lo_s)) : 4096;
         }
         d.cos_decj = hs.binary ? hs.cos_decj : 1.0;
         d.inv_cos_decj = 1.0 / d.cos_decj;
@@ -1265,15 +1469,20 @@ int stn_destroy(StnCtx* ctx) {
     cudaSetDevice(ctx->device);
     for (void* p : ctx->dev_allocs) cudaFree(p);
     for (void* p : ctx->prior_allocs) cudaFree(p);
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < 1 + StnCtx::kSlots; ++i)
         if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     if (ctx->small_in) cudaFreeHost(ctx->small_in);
     if (ctx->small_out) cudaFreeHost(ctx->small_out);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < StnCtx::kSlots; ++i) {
         if (ctx->stage_theta[i]) cudaFree(ctx->stage_theta[i]);
         if (ctx->stage_out[i]) cudaFree(ctx->stage_out[i]);
+        if (ctx->pin_theta[i]) cudaFreeHost(ctx->pin_theta[i]);
+        if (ctx->pin_out[i]) cudaFreeHost(ctx->pin_out[i]);
+        if (ctx->h2d_done[i]) cudaEventDestroy(ctx->h2d_done[i]);
+        if (ctx->d2h_done[i]) cudaEventDestroy(ctx->d2h_done[i]);
         if (ctx->streams[i]) cudaStreamDestroy(ctx->streams[i]);
     }
+    if (ctx->gather_buf) cudaFree(ctx->gather_buf);
     if (ctx->timing_stream) cudaStreamDestroy(ctx->timing_stream);
     delete ctx;
     return STN_OK;
@@ -1325,11 +1534,8 @@ int stn_set_prior(StnCtx* ctx, const StnPrior* pr) {
             return fail(STN_ERR_INVALID, "sin limit %d: bad column", k);
     STN_CUDA(cudaSetDevice(ctx->device));
     STN_CUDA(cudaDeviceSynchronize());                 // no launch may still read the old prior
+    // only the previous prior's arrays are replaced; scratch / staging buffers stay as they are
     for (void* p : ctx->prior_allocs) cudaFree(p);
-    for (int i = 0; i < 3; ++i)
-        if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
-    if (ctx->small_in) cudaFreeHost(ctx->small_in);
-    if (ctx->small_out) cudaFreeHost(ctx->small_out);
     ctx->prior_allocs.clear();
     ctx->has_prior = false;
     ProbDev P = ctx->prob;
@@ -1379,21 +1585,27 @@ int stn_loglike_timed(StnCtx* ctx, const double* theta_dev, int64_t n, int64_t l
     if (steps <= 0 || !total_ms) return fail(STN_ERR_INVALID, "bad steps / null total_ms");
     STN_CUDA(cudaSetDevice(ctx->device));
     if (!ctx->timing_stream) STN_CUDA(cudaStreamCreateWithFlags(&ctx->timing_stream, cudaStreamNonBlocking));
-    cudaEvent_t e0, e1;
-    STN_CUDA(cudaEventCreate(&e0));
-    STN_CUDA(cudaEventCreate(&e1));
-    STN_CUDA(cudaDeviceSynchronize());
-    STN_CUDA(cudaEventRecord(e0, ctx->timing_stream));
-    for (int i = 0; i < steps; ++i) {
-        rc = launch_loglike(ctx, theta_dev, n, ld, layout, mode, plan, out_dev, ctx->timing_stream);
-        if (rc) return rc;
-    }
-    STN_CUDA(cudaEventRecord(e1, ctx->timing_stream));
-    STN_CUDA(cudaEventSynchronize(e1));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
     float ms = 0.f;
-    STN_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
+    auto run = [&]() -> int {
+        STN_CUDA(cudaEventCreate(&e0));
+        STN_CUDA(cudaEventCreate(&e1));
+        STN_CUDA(cudaDeviceSynchronize());
+        STN_CUDA(cudaEventRecord(e0, ctx->timing_stream));
+        for (int i = 0; i < steps; ++i) {
+            const int r = launch_loglike(ctx, theta_dev, n, ld, layout, mode, plan, out_dev, ctx->timing_stream);
+            if (r) return r;
+        }
+        STN_CUDA(cudaEventRecord(e1, ctx->timing_stream));
+        STN_CUDA(cudaEventSynchronize(e1));
+        STN_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        return STN_OK;
+    };
+    rc = run();
+    if (rc) cudaStreamSynchronize(ctx->timing_stream);    // nothing of this call may still be running on return
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (rc) return rc;
     *total_ms = ms;
     return STN_OK;
 }
@@ -1404,72 +1616,184 @@ int stn_loglike_host(StnCtx* ctx, const double* theta_host, int64_t n, int64_t l
     if (rc) return rc;
     if (n == 0) return STN_OK;
     STN_CUDA(cudaSetDevice(ctx->device));
-    const int P = ctx->prob.n_params;
-    for (int i = 0; i < 2; ++i)
-        if (!ctx->streams[i]) STN_CUDA(cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking));
-    // Small batches (a sampler evaluating one point, or a few walkers) are latency-bound: skip both
-    // cudaMemcpy calls by letting the kernel read the parameters from, and write log L to, pinned
-    // mapped host memory.  One launch + one stream synchronise.
-    constexpr int64_t kSmallBytes = 64 * 1024, kSmallRows = 2048;
-    if (layout == STN_LAYOUT_AOS && n <= kSmallRows && n * P * (int64_t)sizeof(double) <= kSmallBytes) {
-        if (!ctx->small_in) {
-            STN_CUDA(cudaHostAlloc((void**)&ctx->small_in, kSmallBytes, cudaHostAllocMapped));
-            STN_CUDA(cudaHostAlloc((void**)&ctx->small_out, kSmallRows * sizeof(double), cudaHostAllocMapped));
-        }
-        for (int64_t i = 0; i < n; ++i) std::memcpy(ctx->small_in + i * P, theta_host + i * ld, (size_t)P * sizeof(double));
-        rc = launch_loglike(ctx, ctx->small_in, n, P, layout, mode, plan, ctx->small_out, ctx->streams[0], 0, 1);
-        if (rc) return rc;
-        STN_CUDA(cudaStreamSynchronize(ctx->streams[0]));
-        std::memcpy(out_host, ctx->small_out, (size_t)n * sizeof(double));
-        return STN_OK;
-    }
-    // chunk so that copies of chunk i+1 overlap the kernel of chunk i
-    int64_t rows = n;
-    const int64_t max_rows = (int64_t)1 << 18;
-    if (rows > max_rows) rows = max_rows;
-    if (ctx->stage_rows < rows) {
-        for (int i = 0; i < 2; ++i) {
-            if (ctx->stage_theta[i]) cudaFree(ctx->stage_theta[i]);
-            if (ctx->stage_out[i]) cudaFree(ctx->stage_out[i]);
-            ctx->stage_theta[i] = ctx->stage_out[i] = nullptr;
-        }
-        ctx->stage_rows = 0;
-        for (int i = 0; i < 2; ++i) {
-            STN_CUDA(cudaMalloc(&ctx->stage_theta[i], (size_t)rows * P * sizeof(double)));
-            STN_CUDA(cudaMalloc(&ctx->stage_out[i], (size_t)rows * sizeof(double)));
-        }
-        ctx->stage_rows = rows;
-    }
     if (mode == STN_MODE_FAST && plan == 0) plan = pick_plan(ctx, n);    // from the whole batch
-    int k = 0;
-    for (int64_t lo = 0; lo < n; lo += rows, ++k) {
-        const int64_t m = (n - lo) < rows ? (n - lo) : rows;
-        cudaStream_t st = ctx->streams[k & 1];
-        double* dth = ctx->stage_theta[k & 1];
-        double* dout = ctx->stage_out[k & 1];
-        int64_t dld;
-        if (layout == STN_LAYOUT_AOS && ld == P) {
-            STN_CUDA(cudaMemcpyAsync(dth, theta_host + lo * ld, (size_t)m * P * sizeof(double),
-                                     cudaMemcpyHostToDevice, st));
-            dld = P;
-        } else if (layout == STN_LAYOUT_AOS) {
-            // padded rows: keep only the first P columns of each
-            STN_CUDA(cudaMemcpy2DAsync(dth, (size_t)P * sizeof(double), theta_host + lo * ld,
-                                       (size_t)ld * sizeof(double), (size_t)P * sizeof(double), (size_t)m,
-                                       cudaMemcpyHostToDevice, st));
-            dld = P;
-        } else {
-            STN_CUDA(cudaMemcpy2DAsync(dth, (size_t)m * sizeof(double), theta_host + lo,
-                                       (size_t)ld * sizeof(double), (size_t)m * sizeof(double), (size_t)P,
-                                       cudaMemcpyHostToDevice, st));
-            dld = m;
+    return run_host(ctx, theta_host, n, ld, layout, mode, plan, out_host);
+}
+
+// ---------------------------------------------------------------------------------
+// Several devices as one (single process, e.g. one sampler): contiguous slices of the batch, one
+// per device, every device holding the full epoch tables.  No collective: for host batches each
+// device DMAs its slice of the result straight into the caller's array; for device-resident
+// slices the results are gathered with peer copies (NVLink) into one buffer.
+// ---------------------------------------------------------------------------------
+int stn_multi_create(const StnProblem* pb, const int* devices, int n_devices, StnMulti** out) {
+    if (!pb || !devices || !out) return fail(STN_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (n_devices <= 0 || n_devices > 64) return fail(STN_ERR_INVALID, "bad device count %d", n_devices);
+    StnMulti* m = new (std::nothrow) StnMulti();
+    if (!m) return fail(STN_ERR_NOMEM, "out of host memory");
+    for (int g = 0; g < n_devices; ++g) {
+        StnCtx* c = nullptr;
+        const int rc = stn_create(pb, devices[g], &c);
+        if (rc) {
+            stn_multi_destroy(m);
+            return rc;
         }
-        rc = launch_loglike(ctx, dth, m, dld, layout, mode, plan, dout, st, 0, 1 + (k & 1));
-        if (rc) return rc;
-        STN_CUDA(cudaMemcpyAsync(out_host + lo, dout, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
+        m->ctx.push_back(c);
     }
-    STN_CUDA(cudaStreamSynchronize(ctx->streams[0]));
-    STN_CUDA(cudaStreamSynchronize(ctx->streams[1]));
+    // direct peer copies for stn_multi_loglike_dev (an already-enabled pair is not an error)
+    for (int a = 0; a < n_devices; ++a)
+        for (int b = 0; b < n_devices; ++b) {
+            if (devices[a] == devices[b]) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, devices[a], devices[b]) == cudaSuccess && can) {
+                cudaSetDevice(devices[a]);
+                cudaDeviceEnablePeerAccess(devices[b], 0);
+            }
+            (void)cudaGetLastError();
+        }
+    *out = m;
+    return STN_OK;
+}
+
+int stn_multi_destroy(StnMulti* m) {
+    if (!m) return STN_OK;
+    for (StnCtx* c : m->ctx) stn_destroy(c);
+    delete m;
+    return STN_OK;
+}
+
+int stn_multi_size(StnMulti* m) { return m ? (int)m->ctx.size() : 0; }
+
+StnCtx* stn_multi_ctx(StnMulti* m, int i) {
+    if (!m || i < 0 || i >= (int)m->ctx.size()) return nullptr;
+    return m->ctx[i];
+}
+
+int64_t stn_multi_launch_count(StnMulti* m) {
+    int64_t t = 0;
+    if (m) for (StnCtx* c : m->ctx) t += c->launches;
+    return t;
+}
+
+int stn_multi_slice(int64_t n, int n_parts, int part, int64_t* lo, int64_t* hi) {
+    if (n < 0 || n_parts <= 0 || part < 0 || part >= n_parts || !lo || !hi) return fail(STN_ERR_INVALID, "bad slice request");
+    const int64_t base = n / n_parts, extra = n % n_parts;
+    *lo = part * base + (part < extra ? part : extra);
+    *hi = *lo + base + (part < extra ? 1 : 0);
+    return STN_OK;
+}
+
+int stn_multi_loglike_host(StnMulti* m, const double* theta_host, int64_t n, int64_t ld, int layout,
+                           int mode, int plan, double* out_host) {
+    if (!m || m->ctx.empty()) return fail(STN_ERR_INVALID, "null multi-context");
+    int rc = check_call(m->ctx[0], theta_host, n, ld, layout, mode, out_host);
+    if (rc) return rc;
+    if (n == 0) return STN_OK;
+    // the plan fixes the summation order: chosen from the WHOLE batch so that the bits do not depend on
+    // how many devices share it (R, the samples per thread, never changes a bit)
+    if (mode == STN_MODE_FAST && plan == 0) plan = pick_plan(m->ctx[0], n);
+    // devices used: a slice below 2^15 rows does not fill one B200
+    int G = (int)m->ctx.size();
+    const int64_t want = n >> 15;
+    if (want < G) G = want < 1 ? 1 : (int)want;
+    if (G == 1) {
+        STN_CUDA(cudaSetDevice(m->ctx[0]->device));
+        return run_host(m->ctx[0], theta_host, n, ld, layout, mode, plan, out_host);
+    }
+    std::vector<int> rcs(G, STN_OK);
+    std::vector<std::string> errs(G);
+    auto work = [&](int g) {
+        int64_t lo = 0, hi = 0;
+        stn_multi_slice(n, G, g, &lo, &hi);
+        StnCtx* c = m->ctx[g];
+        if (cudaSetDevice(c->device) != cudaSuccess) {
+            rcs[g] = STN_ERR_CUDA;
+            errs[g] = "cudaSetDevice failed";
+            return;
+        }
+        const double* th = layout == STN_LAYOUT_AOS ? theta_host + lo * ld : theta_host + lo;
+        rcs[g] = run_host(c, th, hi - lo, ld, layout, mode, plan, out_host + lo);
+        if (rcs[g]) errs[g] = g_err;                    // g_err is thread-local
+    };
+    std::vector<std::thread> pool;
+    pool.reserve(G - 1);
+    for (int g = 1; g < G; ++g) pool.emplace_back(work, g);
+    work(0);
+    for (std::thread& t : pool) t.join();
+    cudaSetDevice(m->ctx[0]->device);
+    for (int g = 0; g < G; ++g)
+        if (rcs[g]) return fail(rcs[g], "device slice %d: %s", g, errs[g].c_str());
+    return STN_OK;
+}
+
+int stn_multi_loglike_dev(StnMulti* m, const double* const* theta_dev, const int64_t* counts, int64_t ld,
+                          int layout, int mode, int plan, double* out_dev, int out_device) {
+    if (!m || m->ctx.empty() || !theta_dev || !counts) return fail(STN_ERR_INVALID, "null argument");
+    const int G = (int)m->ctx.size();
+    int64_t n = 0;
+    for (int g = 0; g < G; ++g) {
+        if (counts[g] < 0) return fail(STN_ERR_INVALID, "negative slice size");
+        if (counts[g] > 0 && !theta_dev[g]) return fail(STN_ERR_INVALID, "null slice");
+        n += counts[g];
+    }
+    if (n == 0) return STN_OK;
+    if (!out_dev) return fail(STN_ERR_INVALID, "null output");
+    if (layout != STN_LAYOUT_AOS && layout != STN_LAYOUT_SOA) return fail(STN_ERR_INVALID, "bad layout %d", layout);
+    if (mode != STN_MODE_FAST && mode != STN_MODE_STRICT) return fail(STN_ERR_INVALID, "bad mode %d", mode);
+    if (mode == STN_MODE_FAST && plan == 0) plan = pick_plan(m->ctx[0], n);      // from the whole batch
+    int rc = STN_OK;
+    int64_t off = 0;
+    for (int g = 0; g < G && !rc; ++g) {
+        StnCtx* c = m->ctx[g];
+        const int64_t cnt = counts[g];
+        if (cnt == 0) continue;
+        if ((rc = check_call(c, theta_dev[g], cnt, ld, layout, mode, out_dev))) break;
+        STN_CUDA(cudaSetDevice(c->device));
+        if ((rc = host_pipe_init(c))) break;
+        cudaStream_t st = c->streams[0];
+        if (c->device == out_device) {
+            rc = launch_loglike(c, theta_dev[g], cnt, ld, layout, mode, plan, out_dev + off, st, 0, 1);
+        } else {
+            if (c->gather_elems < cnt) {
+                STN_CUDA(cudaStreamSynchronize(st));
+                if (c->gather_buf) cudaFree(c->gather_buf);
+                c->gather_buf = nullptr;
+                c->gather_elems = 0;
+                STN_CUDA(cudaMalloc(&c->gather_buf, (size_t)cnt * sizeof(double)));
+                c->gather_elems = cnt;
+            }
+            rc = launch_loglike(c, theta_dev[g], cnt, ld, layout, mode, plan, c->gather_buf, st, 0, 1);
+            if (!rc) {
+                const cudaError_t e = cudaMemcpyPeerAsync(out_dev + off, out_device, c->gather_buf, c->device,
+                                                          (size_t)cnt * sizeof(double), st);
+                if (e != cudaSuccess) rc = fail(STN_ERR_CUDA, "peer copy %d -> %d failed: %s", c->device, out_device,
+                                                cudaGetErrorString(e));
+            }
+        }
+        off += cnt;
+    }
+    // synchronous on return (also after an error: nothing may still be running)
+    for (int g = 0; g < G; ++g) {
+        StnCtx* c = m->ctx[g];
+        if (c->streams[0]) {
+            cudaSetDevice(c->device);
+            const cudaError_t e = cudaStreamSynchronize(c->streams[0]);
+            if (e != cudaSuccess && !rc) rc = fail(STN_ERR_CUDA, "device %d: %s", c->device, cudaGetErrorString(e));
+        }
+    }
+    cudaSetDevice(m->ctx[0]->device);
+    return rc;
+}
+
+int stn_host_register(void* ptr, int64_t bytes) {
+    if (!ptr || bytes <= 0) return fail(STN_ERR_INVALID, "bad argument");
+    STN_CUDA(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
+    return STN_OK;
+}
+
+int stn_host_unregister(void* ptr) {
+    if (ptr) STN_CUDA(cudaHostUnregister(ptr));
     return STN_OK;
 }
 
@@ -1483,6 +1807,9 @@ int stn_model(StnCtx* ctx, int source, const double* theta_dev, int64_t n, int64
     STN_CUDA(cudaSetDevice(ctx->device));
     const int64_t grid = (total + kThreads - 1) / kThreads;
     if (grid > 0x7fffffffLL) return fail(STN_ERR_INVALID, "batch too large for one launch");
+    STN_DBG_RANGE(theta_dev, dbg_theta_bytes(n, ld, layout, ctx->prob.n_params), "theta");
+    STN_DBG_RANGE(radec_dev, (size_t)total * 2 * sizeof(double), "radec");
+    if (off_mas_dev) STN_DBG_RANGE(off_mas_dev, (size_t)total * 2 * sizeof(double), "off_mas");
     (void)cudaGetLastError();
     stn_model_kernel<<<(unsigned)grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         ctx->prob, source, theta_dev, n, ld, layout, mode, radec_dev, off_mas_dev);
@@ -1526,7 +1853,7 @@ int stn_stretch_accept(int device, double* x_dev, double* lp_dev, int64_t n_walk
 
 int stn_host_alloc(void** ptr, int64_t bytes) {
     if (!ptr || bytes < 0) return fail(STN_ERR_INVALID, "bad argument");
-    STN_CUDA(cudaHostAlloc(ptr, (size_t)(bytes ? bytes : 1), cudaHostAllocDefault));
+    STN_CUDA(cudaHostAlloc(ptr, (size_t)(bytes ? bytes : 1), cudaHostAllocPortable));
     return STN_OK;
 }
 

@@ -10,7 +10,7 @@ import numpy as np
 
 from . import _lib
 from .constants import SENTINEL, ROOTS
-from .problem import CompiledProblem, DeviceContext
+from .problem import CompiledProblem, DeviceContext, MultiDeviceContext
 from .shares import filter_dictionary_of_parameter_with_index
 
 try:                                            # bilby is optional: samplers need it, the math does not
@@ -63,6 +63,9 @@ class Gaussianlikelihood(_LikelihoodBase):
     for signature compatibility and ignored: the model is the device kernel.
     Keyword-only extras: earth_provider / earth_xyz (ephemeris.py), device, mode
     ('fast' | 'strict'), plan (0 = automatic; see stn_loglike in include/sterne_b200.h).
+    `device` is a CUDA ordinal or a list of them: with a list, host (numpy) batches are cut into
+    contiguous slices over all listed GPUs from this one process (stn_multi_loglike_host) and a
+    vector's log L has the same bits as on one GPU; everything else runs on the first device.
     """
 
     def __init__(self, refepoch, list_of_dict_timing, list_of_dict_VLBI, shares, positions=None,
@@ -79,7 +82,14 @@ class Gaussianlikelihood(_LikelihoodBase):
         self.DoD_additional_constraints = DoD_additional_constraints
         self.dict_sin_incl_Gaussian_constraints = DoD_additional_constraints['sin_incl_Gaussian_constraints']
         self.a1dot_constraints = a1dot_constraints
-        self.device = int(device)
+        if isinstance(device, (list, tuple)):
+            self.devices = [int(d) for d in device]
+            if not self.devices:
+                raise ValueError('device list is empty')
+        else:
+            self.devices = [int(device)]
+        self.device = self.devices[0]
+        self._multis = {}
         self.mode = _lib.MODES[mode]
         self.plan = int(plan)
         needs_px = any(int(v) >= 0 for v in shares[7])
@@ -109,6 +119,15 @@ class Gaussianlikelihood(_LikelihoodBase):
             if k is None:
                 self._contexts[tuple(problem.default_names)] = ctx
         return ctx
+
+    def _multi(self, keys):
+        """Multi-device context (one StnMulti) for column order `keys`; only with a device list."""
+        ctx = self._context(keys)
+        k = tuple(ctx.problem.names)
+        m = self._multis.get(k)
+        if m is None:
+            m = self._multis[k] = MultiDeviceContext(ctx.problem, self.devices)
+        return m
 
     @property
     def parameter_names(self):
@@ -181,7 +200,40 @@ class Gaussianlikelihood(_LikelihoodBase):
         elif (not isinstance(out, np.ndarray) or out.dtype != np.float64 or out.shape != (n,)
               or not out.flags['C_CONTIGUOUS'] or not out.flags['WRITEABLE']):
             raise TypeError('out must be a writable C-contiguous float64 array of shape (%d,)' % n)
-        ctx.loglike_host_ptr(theta.ctypes.data, n, ld, lay, mode, plan, out.ctypes.data)
+        target = self._multi(keys) if len(self.devices) > 1 else ctx
+        target.loglike_host_ptr(theta.ctypes.data, n, ld, lay, mode, plan, out.ctypes.data)
+        return out
+
+    def log_likelihood_sharded(self, thetas, out=None, keys=None, mode=None, plan=None):
+        """Device-resident slices, one (n_g, P) float64 CUDA tensor per listed device (in device
+        order; empty slices allowed), evaluated where they live; the (sum n_g,) result is gathered
+        with peer copies into `out` (default: a new tensor on the first device).  The plan comes
+        from the total batch size, so the bits equal those of one GPU evaluating the whole batch."""
+        import torch
+        if len(thetas) != len(self.devices):
+            raise ValueError('one tensor per device is needed (%d devices)' % len(self.devices))
+        multi = self._multi(keys)
+        P = multi.problem.n_params
+        mode = self.mode if mode is None else _lib.MODES[mode]
+        plan = self.plan if plan is None else int(plan)
+        ptrs, counts, keep = [], [], []
+        for t, d in zip(thetas, self.devices):
+            if (not _is_torch_tensor(t) or not t.is_cuda or t.device.index != d or t.dtype != torch.float64
+                    or t.dim() != 2 or t.shape[1] != P):
+                raise TypeError('slice for cuda:%d must be an (n, %d) float64 tensor on that device' % (d, P))
+            t = t.contiguous()
+            keep.append(t)
+            ptrs.append(t.data_ptr() if t.shape[0] else 0)
+            counts.append(int(t.shape[0]))
+        total = sum(counts)
+        if out is None:
+            out = torch.empty(total, dtype=torch.float64, device=torch.device('cuda', self.devices[0]))
+        elif (not _is_torch_tensor(out) or not out.is_cuda or out.dtype != torch.float64 or out.numel() != total
+              or not out.is_contiguous()):
+            raise TypeError('out must be a contiguous float64 CUDA tensor of %d elements' % total)
+        for d in set(self.devices) | {out.device.index}:
+            torch.cuda.synchronize(d)                     # producers of the slices / earlier users of out
+        multi.loglike_dev_ptrs(ptrs, counts, P, _lib.LAYOUT_AOS, mode, plan, out.data_ptr(), out.device.index)
         return out
 
     def log_posterior_batch(self, theta, prior, out=None, mode=None, plan=None):
@@ -274,6 +326,7 @@ class Gaussianlikelihood(_LikelihoodBase):
     def __getstate__(self):
         state = dict(self.__dict__)
         state['_contexts'] = {}
+        state['_multis'] = {}
         state['_one'] = None
         return state
 
@@ -288,6 +341,9 @@ class Gaussianlikelihood(_LikelihoodBase):
                 ctx.close()
         self._contexts = {}
         self._one = None
+        for m in self._multis.values():
+            m.close()
+        self._multis = {}
 
 
 # ------------------------------------------------------------------------------------

@@ -91,6 +91,9 @@ class CompiledProblem(object):
             fast[:, 9] = sys_[E:] ** 2
             strict[:, 8], strict[:, 9] = rnd[:E], rnd[E:]
             strict[:, 10], strict[:, 11] = sys_[:E], sys_[E:]
+            # a sampled efac of exactly -999 falls back to 'errs' (simulate.py:318-320)
+            errs_off = (errs ** 2) ** 0.5
+            strict[:, 6], strict[:, 7] = errs_off[:E], errs_off[E:]
         else:
             errs_new = (errs ** 2) ** 0.5                            # simulate.py:319-320
             fast[:, 6] = 1.0 / errs_new[:E]
@@ -254,6 +257,90 @@ class DeviceContext(object):
         _lib.check(self.lib.stn_loglike_timed(self.handle, theta_ptr, n, ld, layout, mode, plan, out_ptr,
                                               steps, ctypes.byref(ms)))
         return ms.value
+
+
+class MultiDeviceContext(object):
+    """Owns one StnMulti: the same CompiledProblem on several GPUs of this box, driven from this
+    one process (include/sterne_b200.h, stn_multi_*).  Host batches are cut into contiguous slices,
+    every device copies its slice of the result straight into the caller's array."""
+
+    def __init__(self, problem, devices):
+        self.lib = _lib.load()
+        self.problem = problem
+        self.devices = [int(d) for d in devices]
+        if not self.devices:
+            raise ValueError('at least one device is needed')
+        pb, keep = problem.as_ctypes()
+        handle = ctypes.c_void_p()
+        arr = (ctypes.c_int32 * len(self.devices))(*self.devices)
+        _lib.check(self.lib.stn_multi_create(ctypes.byref(pb), arr, len(self.devices), ctypes.byref(handle)))
+        del keep
+        self.handle = handle
+
+    def close(self):
+        if getattr(self, 'handle', None):
+            self.lib.stn_multi_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return len(self.devices)
+
+    def auto_plan(self, n):
+        """Plan for a batch of n, always taken from the WHOLE batch (device 0's context decides)."""
+        return int(self.lib.stn_auto_plan(self.lib.stn_multi_ctx(self.handle, 0), n))
+
+    def launch_count(self):
+        return int(self.lib.stn_multi_launch_count(self.handle))
+
+    def slice(self, n, part, n_parts=None):
+        lo, hi = ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(self.lib.stn_multi_slice(n, len(self.devices) if n_parts is None else n_parts, part,
+                                            ctypes.byref(lo), ctypes.byref(hi)))
+        return lo.value, hi.value
+
+    def loglike_host_ptr(self, theta_ptr, n, ld, layout, mode, plan, out_ptr):
+        _lib.check(self.lib.stn_multi_loglike_host(self.handle, theta_ptr, n, ld, layout, mode, plan, out_ptr))
+
+    def loglike_dev_ptrs(self, theta_ptrs, counts, ld, layout, mode, plan, out_ptr, out_device):
+        G = len(self.devices)
+        if len(theta_ptrs) != G or len(counts) != G:
+            raise ValueError('one slice per device is needed (%d devices)' % G)
+        tp = (ctypes.c_void_p * G)(*[ctypes.c_void_p(int(p) if p else 0) for p in theta_ptrs])
+        cn = (ctypes.c_int64 * G)(*[int(c) for c in counts])
+        _lib.check(self.lib.stn_multi_loglike_dev(self.handle, tp, cn, ld, layout, mode, plan, out_ptr,
+                                                  int(out_device)))
+
+
+def host_register(array):
+    """Pins a numpy array in place (cudaHostRegister) so that every GPU can DMA from / into it;
+    returns a handle whose .release() (or garbage collection) unpins it.  Worth it for buffers a
+    sampler reuses: a pageable buffer is staged through the library's pinned ring instead."""
+    lib = _lib.load()
+
+    class _Pinned(object):
+        def __init__(self, a):
+            self.array = a
+            self.ptr = a.ctypes.data
+            _lib.check(lib.stn_host_register(self.ptr, a.nbytes))
+
+        def release(self):
+            if self.ptr:
+                lib.stn_host_unregister(self.ptr)
+                self.ptr = 0
+
+        def __del__(self):
+            try:
+                self.release()
+            except Exception:
+                pass
+
+    return _Pinned(array)
 
 
 def fp64_peak(device=0, iters=1 << 16, reps=5):

@@ -131,20 +131,57 @@ def log_prob_fn(likelihood, prior):
 
 
 class BatchPool(object):
-    """`pool.map(fn, list_of_points)` -> one batched GPU call.  Use with samplers that
-    evaluate several points per iteration through a pool (dynesty: pool=BatchPool(like, keys),
-    queue_size=K).  `fn` is ignored when it is the sampler's own likelihood wrapper: the batch
-    goes to `likelihood.log_likelihood_batch`."""
+    """`pool.map(fn, list_of_points)` -> one batched GPU call, for samplers that evaluate several
+    points per iteration through a pool (dynesty `pool=..., queue_size=K`; bilby `npool`).
+
+        pool = BatchPool(like, prior.keys)
+        sampler = dynesty.NestedSampler(pool.loglike, prior_transform, ndim, pool=pool, queue_size=256)
+
+    Samplers send MORE than likelihood calls through `pool.map` (dynesty maps its proposal /
+    evolution functions and the prior transform too), so only calls whose `fn` is the likelihood are
+    batched: `pool.loglike` itself, a callable registered with `register(fn)`, or a wrapper object
+    that holds one of those in a `loglikelihood`, `func`, `fn` or `__wrapped__` attribute (how
+    dynesty and functools wrap it).  Every other `fn` is applied point by point, as a serial pool would."""
+
+    _WRAPPER_ATTRS = ('loglikelihood', 'func', 'fn', '__wrapped__')
 
     def __init__(self, likelihood, keys, size=1024):
         self.like = likelihood
         self.keys = list(keys)
         self.size = int(size)
+        self._known = []
+
+        def loglike(theta):
+            theta = np.asarray(theta, dtype=np.float64)
+            if theta.ndim == 1:
+                return float(self.like.log_likelihood_batch(theta[None, :], keys=self.keys)[0])
+            return self.like.log_likelihood_batch(theta, keys=self.keys)
+
+        self.loglike = loglike
+        self.register(loglike)
+
+    def register(self, fn):
+        """Declare `fn` (the callable handed to the sampler as its log-likelihood) as batchable."""
+        self._known.append(fn)
+        return fn
+
+    def _is_loglike(self, fn, depth=0):
+        if any(fn is k for k in self._known):
+            return True
+        if depth >= 3:
+            return False
+        for attr in self._WRAPPER_ATTRS:
+            inner = getattr(fn, attr, None)
+            if inner is not None and inner is not fn and self._is_loglike(inner, depth + 1):
+                return True
+        return False
 
     def map(self, fn, points):
         pts = list(points)
         if len(pts) == 0:
             return []
+        if not self._is_loglike(fn):
+            return [fn(p) for p in pts]
         theta = np.asarray(pts, dtype=np.float64).reshape(len(pts), -1)
         return list(self.like.log_likelihood_batch(theta, keys=self.keys))
 

@@ -188,11 +188,20 @@ def config2():
     return _single('config2', 1, with_efac=True)
 
 
-def config3(variant='plain'):
-    """binary pulsar, 8 parameters incl. Omega_asc and inclination (Tempo2 reflex)."""
+def config3(variant='efac'):
+    """binary pulsar, 8 parameters incl. Omega_asc and inclination (Tempo2 reflex).
+
+    'efac' is BASELINE config 3 as written: config 2's six parameters (EFAC on) plus incl_0 and
+    om_asc_0, P = 8, parfile of SURVEY 8(d).  'plain' / 'wide' / 'dots' are the same source
+    without EFAC (P = 7): the survey's orbit, a wide orbit, and OMDOT/PBDOT/A1DOT + constraints."""
     b = dict(PARFILE_CFG3)
     kw = {}
-    if variant == 'wide':          # a wide orbit so the reflex term is a visible fraction of a mas
+    if variant == 'efac':
+        kw = dict(with_efac=True)
+    elif variant == 'efac_wide':   # EFAC + a reflex term that is a visible fraction of a mas
+        b.update(pb=175.46, ecc=0.3, a1=55.33, t0=56100.25, om=50.7)
+        kw = dict(with_efac=True)
+    elif variant == 'wide':          # a wide orbit so the reflex term is a visible fraction of a mas
         b.update(pb=175.46, ecc=0.3, a1=55.33, t0=56100.25, om=50.7)
     elif variant == 'dots':
         b.update(pb=175.46, ecc=0.3, a1=55.33, t0=56100.25, om=50.7, omdot=0.0123, pbdot=1.2e-11, a1dot=3.4e-14)

@@ -62,3 +62,17 @@ def logl_err(got, want, scale):
     got = np.asarray(got, dtype=np.float64)
     want = np.asarray(want, dtype=np.float64)
     return np.abs(got - want) / np.maximum(np.abs(want), scale)
+
+
+PARITY_DIR = os.path.join(ROOT, 'gpurun_out', 'parity')
+
+
+def record_parity(tag, stats):
+    """Parity statistics measured by the GPU tests, one JSON file per tag under gpurun_out/parity/
+    (scratch; tools/collect_parity.py assembles them into profiles/rNN_parity.json)."""
+    try:
+        os.makedirs(PARITY_DIR, exist_ok=True)
+        with open(os.path.join(PARITY_DIR, tag.replace('/', '__') + '.json'), 'w') as f:
+            json.dump({'tag': tag, 'stats': stats}, f)
+    except OSError:
+        pass

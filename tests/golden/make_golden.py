@@ -209,7 +209,8 @@ def main():
            'solve_u': [], 'shares_names': [], 'dms2deg': [], 'decyear2mjd': []}
     with tempfile.TemporaryDirectory() as tmp:
         for case in (synthetic.config1(), synthetic.config2(), efad_case(), synthetic.config3('plain'),
-                     synthetic.config3('wide'), synthetic.config3('dots'), synthetic.config4(), sentinel_case()):
+                     synthetic.config3('wide'), synthetic.config3('dots'), synthetic.config4(), sentinel_case(),
+                     synthetic.config3('efac'), synthetic.config3('efac_wide')):
             out['cases'].append(run_case(case, tmp))
             print('case %-16s logL(truth) = %.6f' % (case.name, out['cases'][-1]['ref']['log_likelihood'][0]))
     for e, c in [(0.0, 1.0), (1e-6, 0.3), (0.0794, 12.75), (0.3, -7.1), (0.6, 2.0), (0.9, 1e-3), (0.9, 3.0), (0.3, 500.123)]:

@@ -8,7 +8,8 @@ import sterne_b200 as sb
 from sterne_b200 import synthetic, _lib
 from sterne_b200._lib import make_plan
 from oracle import sterne_oracle as O
-from conftest import rel_err, logl_err, logl_scale
+from oracle import mp_arbiter
+from conftest import rel_err, logl_err, logl_scale, record_parity
 
 pytestmark = pytest.mark.gpu
 
@@ -68,11 +69,64 @@ def test_golden_reference_positions(golden, golden_dir, mode):
         like.close()
 
 
+def _efad_case():
+    """config 2 with EFAD switched on as well (P = 7)."""
+    case = synthetic.config2()
+    shares = [list(r) for r in case.shares]
+    shares[2] = [0]
+    names = list(synthetic.get_parameters_from_shares(shares))
+    truth = dict(case.truth)
+    truth['efad_0'] = synthetic.TRUTH['efad']
+    return synthetic.SyntheticCase('config2_efad', case.refepoch, case.LoD_timing, case.LoD_VLBI, shares,
+                                   case.earth_xyz, truth, synthetic._box_for(names, truth))
+
+
+def _sentinel_case():
+    """2 sources; source 1 has px / mu_a / incl / om_asc absent, so mu_a = -999 is USED AS A NUMBER
+    (positions.py:59,110) -- the golden 'sentinels' case as an in-memory problem."""
+    rng = np.random.default_rng(11)
+    T = synthetic.TRUTH
+    b = dict(synthetic.PARFILE_CFG3)
+    b.update(pb=175.46, ecc=0.3, a1=55.33, t0=56100.25, om=50.7)
+    timing = synthetic.timing_dict(**b)
+    refepoch = 57365.0
+    v0, x0 = synthetic.make_source(rng, refepoch, 57000 + rng.uniform(0, 730, 7), T['ra'], T['dec'], T['mu_a'],
+                                   T['mu_d'], T['px'], timing=timing, incl=T['incl'], om_asc=T['om_asc'])
+    v1, x1 = synthetic.make_source(rng, refepoch, 57000 + rng.uniform(0, 730, 5), T['ra'] + 1e-6, T['dec'] + 1e-6,
+                                   0.0, T['mu_d'], 0.0)
+    shares = [[0, 1], [-1, -1], [-1, -1], [0, -1], [0, -1], [0, 0], [0, -1], [0, -1], [0, 1]]
+    names = list(synthetic.get_parameters_from_shares(shares))
+    truth = {}
+    for k in names:
+        srcs, root = synthetic.parameter_name_to_pmparin_indice(k)
+        truth[k] = T[root] + (1e-6 if (root in ('ra', 'dec') and srcs == [1]) else 0.0)
+    return synthetic.SyntheticCase('sentinels', refepoch, [timing, {}], [v0, v1], shares, [x0, x1], truth,
+                                   synthetic._box_for(names, truth))
+
+
 CASES = {
-    'config1': synthetic.config1, 'config2': synthetic.config2,
+    'config1': synthetic.config1, 'config2': synthetic.config2, 'config2_efad': _efad_case,
+    'config3': lambda: synthetic.config3('efac'), 'config3_efac_wide': lambda: synthetic.config3('efac_wide'),
     'config3_plain': lambda: synthetic.config3('plain'), 'config3_wide': lambda: synthetic.config3('wide'),
-    'config3_dots': lambda: synthetic.config3('dots'), 'config4': synthetic.config4,
+    'config3_dots': lambda: synthetic.config3('dots'), 'config4': synthetic.config4, 'sentinels': _sentinel_case,
 }
+
+
+def _check_parity(tag, case, theta, got, want):
+    """north_star's contract is 1e-10 RELATIVE on log L.  The pure relative error (no floor) is
+    measured and recorded (profiles/r02_parity.json is assembled from these records); every vector
+    above 1e-10 must be explained by the 50-digit arbiter: |log L| below the size of the terms that
+    were summed (log L = -sum ln sigma - chi^2/2 crosses zero inside the prior box) AND the CUDA
+    result no farther from the exact value than the float64 oracle's own rounding noise."""
+    floor = logl_scale(case.LoD_VLBI)
+    stats = mp_arbiter.parity_stats(case, theta, got, want, rtol=LOGL_RTOL, floor=floor)
+    record_parity(tag, stats)
+    assert stats['explained'], (tag, stats['max_rel'], stats['count_above'],
+                                [e for e in stats['exceedances'] if not e['explained']][:3])
+    # and the floored form keeps every vector within 1e-10 of the summed terms' size
+    err = logl_err(got, want, floor)
+    assert err.max() < LOGL_RTOL, (tag, err.max(), int((err > LOGL_RTOL).sum()))
+    return stats
 
 
 @pytest.mark.parametrize('name', list(CASES))
@@ -84,26 +138,33 @@ def test_batch_matches_oracle(name, mode):
     want = _oracle_batch(case, theta)
     like = case.likelihood(mode=mode)
     got = like.log_likelihood_batch(theta)
-    err = logl_err(got, want, logl_scale(case.LoD_VLBI))
-    assert err.max() < LOGL_RTOL, (name, mode, err.max(), int((err > LOGL_RTOL).sum()))
+    _check_parity('%s/%s/4096' % (name, mode), case, theta, got, want)
     like.close()
 
 
-@pytest.mark.parametrize('name', ['config3_dots', 'config4'])
+@pytest.mark.parametrize('name', list(CASES) + ['config5_A', 'config5_C'])
 def test_model_offsets_match_oracle(name):
-    """1e-12 mas on the model offsets (positions.py:114-118), both kernel forms."""
-    case = CASES[name]()
-    theta = case.sample_theta(257, seed=3)
+    """1e-12 mas on the model offsets (positions.py:114-118), both kernel forms, every case."""
+    case = CASES[name]() if name in CASES else synthetic.config5(name[-1])
+    theta = case.sample_theta(257 if name in CASES else 33, seed=3)
     names, idx = O.column_table(case.shares)
+    worst = {}
     for mode in ('fast', 'strict'):
         like = case.likelihood(mode=mode)
+        w = 0.0
         for i in range(len(case.LoD_VLBI)):
             model, off = O.batch_model(case.refepoch, case.LoD_VLBI[i], case.earth_xyz[i], case.LoD_timing[i],
                                        idx[i], theta)
             radec, goff = like.model_positions(theta, i, offsets=True)
-            assert np.abs(goff - off).max() < OFFSET_ATOL_MAS, (name, mode, i, np.abs(goff - off).max())
-            assert np.abs(radec - model).max() <= 2 * np.spacing(6.3)
+            # the sentinel case drives a source with mu_a = -999 mas/yr: |offset| ~ 2000 mas there, one ulp of
+            # it is 2e-13 mas, so the tolerance is 1e-12 mas or 4 ulp of the offset, whichever is larger
+            tol = np.maximum(OFFSET_ATOL_MAS, 4 * np.spacing(np.abs(off)))
+            assert (np.abs(goff - off) <= tol).all(), (name, mode, i, np.abs(goff - off).max())
+            assert np.abs(radec - model).max() <= 2 * np.spacing(np.abs(model).max())
+            w = max(w, float(np.abs(goff - off).max()))
+        worst[mode] = w
         like.close()
+    record_parity('offsets_mas/%s' % name, {'max_abs_mas': worst, 'n': int(theta.shape[0]), 'atol_mas': OFFSET_ATOL_MAS})
 
 
 @pytest.mark.parametrize('variant', ['A', 'B', 'C'])
@@ -117,8 +178,9 @@ def test_config5_shape_matches_oracle(variant):
     for plan in (0, make_plan(1), make_plan(4), make_plan(32), make_plan(1, 8), make_plan(1, 64), make_plan(2, 5)):
         got = like.log_likelihood_batch(theta, plan=plan)
         assert logl_err(got, want, scale).max() < LOGL_RTOL, (variant, plan, logl_err(got, want, scale).max())
+    _check_parity('config5_%s/fast/384' % variant, case, theta, like.log_likelihood_batch(theta), want)
     got = like.log_likelihood_batch(theta, mode='strict')
-    assert logl_err(got, want, scale).max() < LOGL_RTOL
+    _check_parity('config5_%s/strict/384' % variant, case, theta, got, want)
     like.close()
 
 
@@ -442,3 +504,127 @@ def test_likelihood_survives_pickling():
     assert clone.log_likelihood() == like.log_likelihood()
     clone.close()
     like.close()
+
+
+# ------------------------------------------------------------------------------------------
+# round 2: memory safety of one shared context, the host pipeline, several devices in one process
+# ------------------------------------------------------------------------------------------
+def test_one_context_survives_set_prior_between_launches():
+    """Regression for the r01 use-after-free: stn_set_prior used to free the small-batch staging and
+    the split-plan scratch of the context it shares with log_likelihood().  ONE context:
+    log_likelihood() -> set_prior -> log_likelihood() -> split-plan batch (host and device) ->
+    set_prior(another prior) -> logpost -> close(), every value against the oracle."""
+    import torch
+    from sterne_b200.sampler import BoxPrior
+    case = synthetic.config5('C', n_epochs=300)                 # 8 sources x 3 chunks: split plans exist
+    like = case.likelihood()
+    keys = like.parameter_names                                  # same column order -> the SAME context
+    ctx = like._context(None)
+    assert like._context(keys) is ctx
+    theta = case.sample_theta(3000, seed=12, scale=0.3)
+    want = _oracle_batch(case, theta)
+    scale = logl_scale(case.LoD_VLBI)
+
+    def one(k):
+        like.parameters.update(dict(zip(keys, theta[k])))
+        return like.log_likelihood()
+
+    assert abs(one(0) - want[0]) <= LOGL_RTOL * max(abs(want[0]), scale)          # allocates small_in / small_out
+    limits = {k: [float(theta[:, j].min()) - 1.0, float(theta[:, j].max()) + 1.0, 'Uniform'] for j, k in enumerate(keys)}
+    prior1 = BoxPrior(limits, keys=keys)
+    ctx.set_prior(prior1)
+    assert abs(one(1) - want[1]) <= LOGL_RTOL * max(abs(want[1]), scale)          # small-batch staging still alive
+    split = make_plan(1, 6)
+    got = like.log_likelihood_batch(theta, plan=split)                            # host pipeline scratch
+    assert logl_err(got, want, scale).max() < LOGL_RTOL
+    th = torch.from_numpy(theta).cuda()
+    dev = like.log_likelihood_batch(th, plan=split)                               # device-API scratch
+    assert np.array_equal(dev.cpu().numpy(), got)
+    limits2 = dict(limits)
+    limits2[keys[0]] = [float(theta[:, 0].mean()), float(theta[:, 0].std()) + 1e-12, 'Gaussian']
+    prior2 = BoxPrior(limits2, keys=keys)
+    ctx.set_prior(prior2)                                                         # replaces the first prior
+    post = like.log_posterior_batch(th, prior2, plan=split).cpu().numpy()
+    lp = prior2.log_prob(theta)
+    assert np.isfinite(lp).all()
+    assert (np.abs(post - (want + lp)) / np.maximum(np.abs(want + lp), scale)).max() < LOGL_RTOL
+    assert np.array_equal(like.log_likelihood_batch(theta, plan=split), got)      # scratch reused after set_prior
+    assert abs(one(2) - want[2]) <= LOGL_RTOL * max(abs(want[2]), scale)
+    like.close()
+
+
+@pytest.mark.parametrize('n', [4097, (1 << 15) + 5, 3 * (1 << 16) + 17])
+def test_host_pipeline_pageable_pinned_and_layouts(n):
+    """The host entry point (ramped chunks on three streams) gives the device path's bits for pageable
+    numpy arrays (staged through the library's pinned ring), pinned buffers, registered buffers,
+    padded rows and the SoA layout, at sizes that cross several chunk boundaries."""
+    import torch
+    case = synthetic.config4()
+    like = case.likelihood()
+    P = case.n_params
+    theta = case.sample_theta(n, seed=n % 1000)
+    want = like.log_likelihood_batch(torch.from_numpy(theta).cuda(), plan=make_plan(1)).cpu().numpy()
+    got = like.log_likelihood_batch(theta, plan=make_plan(1))                     # pageable in, pageable out
+    assert np.array_equal(got, want)
+    pin_t = torch.empty((n, P), dtype=torch.float64, pin_memory=True)
+    pin_t.copy_(torch.from_numpy(theta))
+    pin_o = torch.empty(n, dtype=torch.float64, pin_memory=True)
+    like.log_likelihood_batch(pin_t.numpy(), out=pin_o.numpy(), plan=make_plan(1))  # pinned in, pinned out
+    assert np.array_equal(pin_o.numpy(), want)
+    out2 = np.empty(n)
+    like.log_likelihood_batch(pin_t.numpy(), out=out2, plan=make_plan(1))           # pinned in, pageable out
+    assert np.array_equal(out2, want)
+    reg = theta.copy()
+    handle = sb.host_register(reg)                                                   # caller's own buffer pinned in place
+    assert np.array_equal(like.log_likelihood_batch(reg, plan=make_plan(1)), want)
+    handle.release()
+    padded = np.zeros((n, P + 3))
+    padded[:, :P] = theta
+    assert np.array_equal(like.log_likelihood_batch(padded[:, :P], plan=make_plan(1)), want)
+    soa = np.ascontiguousarray(theta.T)
+    assert np.array_equal(like.log_likelihood_batch(soa, layout='soa', plan=make_plan(1)), want)
+    soa_wide = np.zeros((P, n + 9))
+    soa_wide[:, :n] = soa
+    assert np.array_equal(like.log_likelihood_batch(soa_wide[:, :n], layout='soa', plan=make_plan(1)), want)
+    like.close()
+
+
+def test_one_process_drives_several_contexts():
+    """Gaussianlikelihood(device=[...]): one process, one (N, P) numpy batch, contiguous slices over
+    the listed devices, bits identical to one device.  A device may be listed twice, which exercises
+    the slicing / threading / peer-gather logic on a single-GPU box; with >= 2 GPUs the real thing runs."""
+    import torch
+    case = synthetic.config5('C', n_epochs=256)
+    n = 3 * (1 << 16) + 11
+    theta = case.sample_theta(n, seed=31, scale=0.3)
+    single = case.likelihood(device=0)
+    want = single.log_likelihood_batch(theta)
+    ngpu = torch.cuda.device_count()
+    lists = [[0, 0], [0, 0, 0]]
+    if ngpu >= 2:
+        lists.append(list(range(ngpu)))
+    for devices in lists:
+        multi = case.likelihood(device=devices)
+        got = multi.log_likelihood_batch(theta)
+        assert np.array_equal(got, want), devices
+        # small batches fall back to fewer devices, same bits
+        assert np.array_equal(multi.log_likelihood_batch(theta[:1000]), single.log_likelihood_batch(theta[:1000]))
+        # device-resident slices, gathered with peer copies into one tensor
+        m = multi._multi(None)
+        parts, off = [], 0
+        for g, d in enumerate(devices):
+            lo, hi = m.slice(n, g)
+            assert lo == off
+            off = hi
+            parts.append(torch.from_numpy(theta[lo:hi]).to(torch.device('cuda', d)))
+        assert off == n
+        gathered = multi.log_likelihood_sharded(parts)
+        assert np.array_equal(gathered.cpu().numpy(), want), devices
+        # strict mode and the dict API still work on a multi-device likelihood
+        assert np.array_equal(multi.log_likelihood_batch(theta[:70000], mode='strict'),
+                              single.log_likelihood_batch(theta[:70000], mode='strict'))
+        multi.parameters.update(dict(zip(multi.parameter_names, theta[5])))
+        single.parameters.update(multi.parameters)
+        assert multi.log_likelihood() == single.log_likelihood()
+        multi.close()
+    single.close()

@@ -128,7 +128,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == {name for name, _, _ in _lib.SYMBOLS}
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.stn_version() == 1
+    assert lib.stn_version() == _lib.ABI_VERSION == int(re.search(r'#define STN_ABI_VERSION (\d+)', header).group(1))
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -41,9 +41,29 @@ def test_batch_pool_is_one_batched_call():
             return theta.sum(axis=1)
 
     pool = BatchPool(Like(), ['a', 'b'])
-    out = pool.map(None, [np.array([1.0, 2.0]), np.array([3.0, 4.0]), np.array([5.0, 6.0])])
-    assert out == [3.0, 7.0, 11.0] and calls == [(3, 2)]
-    assert pool.map(None, []) == []
+    pts = [np.array([1.0, 2.0]), np.array([3.0, 4.0]), np.array([5.0, 6.0])]
+    assert pool.map(pool.loglike, pts) == [3.0, 7.0, 11.0] and calls == [(3, 2)]
+    assert pool.map(pool.loglike, []) == []
+    assert pool.loglike(np.array([1.0, 2.0])) == 3.0             # a single point outside map()
+
+    # a sampler's own wrapper around the likelihood (dynesty keeps it in .loglikelihood) is recognised
+    class Wrapped(object):
+        def __init__(self, f):
+            self.loglikelihood = f
+
+        def __call__(self, x):
+            return self.loglikelihood(x)
+
+    del calls[:]
+    assert pool.map(Wrapped(pool.loglike), pts) == [3.0, 7.0, 11.0] and calls == [(3, 2)]
+    user_fn = pool.register(lambda x: -1.0)                     # explicitly registered callable
+    assert pool.map(user_fn, pts) == [3.0, 7.0, 11.0]
+    # anything else a sampler maps (prior transforms, proposal / evolution functions with tuple
+    # arguments) is applied point by point and never reaches the likelihood
+    del calls[:]
+    assert pool.map(lambda u: 2.0 * u, [np.array([0.5, 1.0])])[0].tolist() == [1.0, 2.0]
+    assert pool.map(lambda args: args[0] + args[1]['k'], [(1, {'k': 2}), (3, {'k': 4})]) == [3, 7]
+    assert calls == []
 
 
 def test_stretch_move_recovers_a_gaussian():
