@@ -157,11 +157,79 @@ def workload_config(n_gpus):
 # --------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the headline kernel, read from the newest
+    committed ncu summary of this command (profiles/rNN_ncu_loglike_fast_C.txt); (bytes, file) or (None, None)."""
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_ncu_loglike_fast_C.txt')))
+    if not files:
+        return None, None
+    text = open(files[-1]).read()
+    tot = 0.0
+    for key in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+        m = re.search(r'^%s\s+(\w+)\s+([0-9.eE+-]+)' % re.escape(key), text, re.M)
+        if not m:
+            return None, None
+        unit = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(m.group(1))
+        if unit is None:
+            return None, None
+        tot += float(m.group(2)) * unit
+    return int(tot), os.path.relpath(files[-1], ROOT)
+
+
+class SharedResult(object):
+    """One (n,) float64 host array shared by all ranks of the box (POSIX shared memory), pinned in every
+    rank: each GPU DMAs its slice of log L straight into it, so the result of an N-GPU evaluation is
+    assembled in ONE host array without a collective.  Falls back to None when /dev/shm is too small."""
+
+    def __init__(self, n, rank, dist, group):
+        import numpy as np
+        from multiprocessing import shared_memory
+        from sterne_b200 import host_register
+        self.shm = None
+        name = [None]
+        if rank == 0:
+            try:
+                st = os.statvfs('/dev/shm')
+                if st.f_bavail * st.f_frsize > 2 * n * 8 + (64 << 20):
+                    self.shm = shared_memory.SharedMemory(create=True, size=n * 8)
+                    name[0] = self.shm.name
+            except Exception:
+                self.shm = None
+        dist.broadcast_object_list(name, src=0, group=group)
+        self.array = None
+        if name[0] is None:
+            return
+        if rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name[0])
+        self.array = np.ndarray((n,), dtype=np.float64, buffer=self.shm.buf)
+        self.pin = host_register(self.array)
+        self.owner = rank == 0
+
+    def close(self):
+        if self.shm is None:
+            return
+        try:
+            self.pin.release()
+        except Exception:
+            pass
+        self.array = None
+        self.pin = None
+        try:
+            self.shm.close()
+            if self.owner:
+                self.shm.unlink()
+        except Exception:
+            pass
+
+
 def run_ours(args, rank, local_rank, world):
+    import numpy as np
     import torch
     import torch.distributed as dist
     from sterne_b200 import synthetic, fp64_peak
-    from sterne_b200.sharding import ShardedLikelihood
+    from sterne_b200.sharding import ShardedLikelihood, shard_bounds
 
     # CPU baseline first (rank 0, N = 1 only), before this process touches CUDA
     cpu_baseline = None
@@ -183,12 +251,16 @@ def run_ours(args, rank, local_rank, world):
 
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device; sterne_b200 has no CPU path')
-    if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'INFO'):
-        os.environ['NCCL_DEBUG'] = 'WARN'          # NCCL's banner goes to stdout; stdout carries the JSON line
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    cpu_group = None
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
+        cpu_group = dist.new_group(backend='gloo')         # host-side barriers that keep the GPUs idle
+
+    def host_barrier():
+        if world > 1:
+            dist.barrier(group=cpu_group)
 
     # weak scaling (default, the contract's): 2^22 vectors per GPU.  --scaling strong: 2^22 vectors in
     # total, 2^22 / world per GPU (SURVEY 8e's reading of the 1 -> 8 GPU target).
@@ -196,72 +268,176 @@ def run_ours(args, rank, local_rank, world):
     case = synthetic.config5('C')
     like = case.likelihood(device=local_rank)
     ctx = like._context(None)
-    evals_per_step_rank = N * case.evals_per_sample
+    E = case.evals_per_sample
+    P = case.n_params
     theta = synthetic.device_theta(case, N, seed=1234 + rank, device=dev)
     out = torch.empty(N, dtype=torch.float64, device=dev)
     sharded = ShardedLikelihood(like) if world > 1 else None
-    gathered = torch.empty(N * world, dtype=torch.float64, device=dev) if world > 1 else None
-    plan = ctx.auto_plan(N * world)
-
-    def step():
-        like.log_likelihood_batch(theta, out=out, plan=plan)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, out)
 
     def sync_all():
-        if world > 1:
-            dist.barrier()
+        torch.cuda.synchronize(dev)
+        host_barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    sync_all()
+    def timed_device_steps(th, n_global, steps, warm):
+        """K steps of: fused likelihood kernel over this rank's slice (+ for N > 1 its epilogue stores into
+        every rank's result buffer over NVLink, then the stream-ordered barrier).  Returns
+        (total ms max over ranks, mean kernel-only ms on this rank, this rank's result tensor, launches)."""
+        n_local = int(th.shape[0])
+        plan = ctx.auto_plan(n_global)
+        res = out[:n_local]
+
+        def one(evs=None):
+            nonlocal res
+            if evs is not None:
+                evs[0].record()
+            if world == 1:
+                like.log_likelihood_batch(th, out=res, plan=plan)
+            else:
+                res = sharded.evaluate_scatter(th, n_global, plan=plan, barrier=False)
+            if evs is not None:
+                evs[1].record()
+            if world > 1:
+                sharded.barrier()
+
+        for _ in range(warm):
+            one()
+        sync_all()
+        l0 = ctx.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kev = []
+        e0.record()
+        for _ in range(steps):
+            kev.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+            one(kev[-1])
+        e1.record()
+        sync_all()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / steps
+        return t.item(), kernel_ms, res, ctx.launch_count() - l0
+
+    warm = max(args.warmup, 3)
+    timed_device_steps(theta, N * world, 1, warm)                 # warm-up (also builds the peer mappings)
     # FP64 roofline denominator, measured with the GPU already warm (37 ms per launch)
     peak_tf, _ = fp64_peak(local_rank, iters=1 << 17, reps=5)
     sync_all()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = ctx.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_events = []
-    sync_all()
-    e0.record()
-    for _ in range(args.steps):
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k0.record()
-        like.log_likelihood_batch(theta, out=out, plan=plan)
-        k1.record()
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, out)
-        kernel_events.append((k0, k1))
-    e1.record()
-    sync_all()
-    ms_total = e0.elapsed_time(e1)
-    kernel_ms = sum(a.elapsed_time(b) for a, b in kernel_events) / args.steps
-    launches = ctx.launch_count() - launches0
+    ms_total, kernel_ms, res_dev, launches = timed_device_steps(theta, N * world, args.steps, 0)
     clocks = sampler.stop() if rank == 0 else None
+    dev_result = res_dev.clone()                                   # (N * world,) for N > 1, (N,) for N = 1
 
-    # ---- end to end: host (pinned) buffers through the public API, copies inside the timed region
-    theta_host = torch.empty((N, case.n_params), dtype=torch.float64, pin_memory=True)
-    theta_host.copy_(theta)
-    out_host = torch.empty(N, dtype=torch.float64, pin_memory=True)
-    th_np, out_np = theta_host.numpy(), out_host.numpy()
-    for _ in range(2):
-        like.log_likelihood_batch(th_np, out=out_np, plan=plan)
-    sync_all()
-    t0 = time.perf_counter()
+    # ---- end to end: HOST buffers through the public API, copies inside the timed region.  N = 1: one call
+    # of Gaussianlikelihood.log_likelihood_batch(numpy) (pinned, then pageable).  N > 1 (one process per GPU):
+    # every rank makes that call on its slice and DMAs its slice of the result into ONE host array shared by
+    # all ranks (POSIX shared memory pinned in every rank): the result is assembled in one place, no collective.
+    def timed_host_steps(th_np, n_global, lo, out_np, steps):
+        plan = ctx.auto_plan(n_global)
+        n_local = th_np.shape[0]
+        for _ in range(2):
+            like.log_likelihood_batch(th_np, out=out_np[lo:lo + n_local], plan=plan)
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            like.log_likelihood_batch(th_np, out=out_np[lo:lo + n_local], plan=plan)   # synchronous: result is on the host
+            host_barrier()                                                               # ... of every rank
+        ms = (time.perf_counter() - t0) * 1e3
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
     e2e_steps = max(2, min(args.steps, 5))
-    for _ in range(e2e_steps):
-        like.log_likelihood_batch(th_np, out=out_np, plan=plan)      # synchronous: result is on the host
-    sync_all()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
-    same = bool(torch.equal(out_host.to(dev), out))
+    theta_host = torch.empty((N, P), dtype=torch.float64, pin_memory=True)
+    theta_host.copy_(theta)
+    th_np = theta_host.numpy()
+    lo_w = rank * N
+    shared = SharedResult(N * world, rank, dist, cpu_group) if world > 1 else None
+    if shared is not None and shared.array is not None:
+        out_np, assembled = shared.array, 'one host array shared by all ranks (POSIX shm, pinned in each rank)'
+    else:
+        out_host = torch.empty(N * world, dtype=torch.float64, pin_memory=True)
+        out_np, assembled = out_host.numpy(), ('rank-local pinned array' if world > 1 else 'the caller\'s pinned array')
+    e2e_ms = timed_host_steps(th_np, N * world, lo_w, out_np, e2e_steps)
+    if shared is not None and shared.array is not None:
+        same = bool(np.array_equal(out_np, dev_result.cpu().numpy())) if rank == 0 else True   # the WHOLE assembled result
+    else:
+        same = bool(np.array_equal(out_np[lo_w:lo_w + N], dev_result[lo_w:lo_w + N].cpu().numpy()))
+    e2e_pageable = None
+    if world == 1:
+        th_page = np.array(th_np, copy=True)                       # ordinary (pageable) numpy arrays, as a sampler has
+        out_page = np.empty(N)
+        pg_ms = timed_host_steps(th_page, N, 0, out_page, e2e_steps)
+        e2e_pageable = {'value': N * E * e2e_steps / (pg_ms * 1e-3), 'unit': UNIT, 'ms_per_step': pg_ms / e2e_steps,
+                        'matches_device_path': bool(np.array_equal(out_page, dev_result.cpu().numpy())),
+                        'note': 'pageable numpy in / out: staged through the library\'s pinned ring (stn_loglike_host)'}
+        del th_page, out_page
 
-    t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
+    # ---- N > 1 extras: bits independent of the GPU count; strong scaling (2^22 vectors in total); ONE process
+    # driving all GPUs
+    sharded_bits_match, strong, single_process = None, None, None
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = t.tolist()
+        n_probe = 1 << 16
+        probe = synthetic.device_theta(case, n_probe, seed=99, device=dev)            # the same batch on every rank
+        one_gpu = like.log_likelihood_batch(probe, plan=ctx.auto_plan(n_probe))
+        fused = sharded.log_likelihood_batch(probe)
+        nccl = sharded.log_likelihood_batch(probe, fused=False)
+        ok = torch.tensor([float(torch.equal(fused, one_gpu) and torch.equal(nccl, one_gpu))], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        sharded_bits_match = bool(ok.item() == 1.0)
+
+        n_tot = 1 << LOG2_N
+        lo_s, hi_s = shard_bounds(n_tot, world, rank)
+        th_s = theta[:hi_s - lo_s]
+        s_ms, s_kernel_ms, s_res, _ = timed_device_steps(th_s, n_tot, args.steps, 2)
+        s_dev = s_res.clone()
+        s_e2e_ms = timed_host_steps(th_np[:hi_s - lo_s], n_tot, lo_s, out_np, e2e_steps)
+        if shared is not None and shared.array is not None:
+            s_same = bool(np.array_equal(out_np[:n_tot], s_dev.cpu().numpy())) if rank == 0 else True
+        else:
+            s_same = bool(np.array_equal(out_np[lo_s:hi_s], s_dev[lo_s:hi_s].cpu().numpy()))
+        strong = {'scaling': 'strong', 'vectors_total': n_tot, 'vectors_per_gpu': hi_s - lo_s,
+                  'value': n_tot * E * args.steps / (s_ms * 1e-3), 'unit': UNIT, 'ms_per_step': s_ms / args.steps,
+                  'kernel_ms': s_kernel_ms,
+                  'e2e': {'value': n_tot * E * e2e_steps / (s_e2e_ms * 1e-3), 'unit': UNIT,
+                          'ms_per_step': s_e2e_ms / e2e_steps, 'h2d_bytes_per_step': n_tot * P * 8,
+                          'd2h_bytes_per_step': n_tot * 8, 'result_assembled_in': assembled,
+                          'matches_device_path': s_same}}
+        # one process, all GPUs (what a single emcee / dynesty process gets): rank 0 drives every device of the
+        # box through Gaussianlikelihood(device=[0..N-1]) while the other ranks wait on a host-side barrier
+        sync_all()
+        if rank == 0:
+            sp_like = case.likelihood(device=list(range(world)))
+            n_tot = int(th_np.shape[0])                               # rank 0's whole host batch (2^22 in the weak run)
+            sp_out = torch.empty(n_tot, dtype=torch.float64, pin_memory=True).numpy()
+            for _ in range(2):
+                sp_like.log_likelihood_batch(th_np, out=sp_out)
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                sp_like.log_likelihood_batch(th_np, out=sp_out)
+            sp_ms = (time.perf_counter() - t0) * 1e3
+            ref_one = like.log_likelihood_batch(theta, plan=ctx.auto_plan(n_tot)).cpu().numpy()
+            th_page = np.array(th_np, copy=True)
+            sp_page = np.empty(n_tot)
+            sp_like.log_likelihood_batch(th_page, out=sp_page)
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                sp_like.log_likelihood_batch(th_page, out=sp_page)
+            sp_page_ms = (time.perf_counter() - t0) * 1e3
+            single_process = {
+                'api': 'Gaussianlikelihood(device=[0..%d]).log_likelihood_batch(numpy (2^22, 22)) -> '
+                       'stn_multi_loglike_host' % (world - 1),
+                'vectors_total': n_tot, 'e2e_value': n_tot * E * e2e_steps / (sp_ms * 1e-3), 'unit': UNIT,
+                'ms_per_step': sp_ms / e2e_steps, 'bits_match_one_gpu': bool(np.array_equal(sp_out, ref_one)),
+                'pageable_e2e_value': n_tot * E * e2e_steps / (sp_page_ms * 1e-3),
+                'pageable_ms_per_step': sp_page_ms / e2e_steps,
+                'pageable_bits_match_one_gpu': bool(np.array_equal(sp_page, ref_one))}
+            sp_like.close()
+            del th_page, sp_page
+        sync_all()
 
     # ---- variants A and B of the same kernel (kernel-only, rank 0, N = 1)
     variants = {}
@@ -291,7 +467,7 @@ def run_ours(args, rank, local_rank, world):
     # ---- batch-size sweep of the headline variant (BASELINE config 5: N = 2^16 .. 2^22), kernel-only
     sweep = {}
     if world == 1 and not args.no_variants:
-        for l2 in (16, 18, 20):
+        for l2 in (16, 17, 18, 19, 20, 21):
             n = 1 << l2
             so = torch.empty(n, dtype=torch.float64, device=dev)
             reps = max(args.steps, 1 << max(0, 20 - l2))
@@ -305,34 +481,41 @@ def run_ours(args, rank, local_rank, world):
             b.record()
             torch.cuda.synchronize(dev)
             ms = a.elapsed_time(b) / reps
-            sweep['2^%d' % l2] = {'ms_per_step': ms, 'evals_per_s': n * case.evals_per_sample / (ms * 1e-3),
-                                  'plan': ctx.auto_plan(n)}
+            sweep['2^%d' % l2] = {'ms_per_step': ms, 'evals_per_s': n * E / (ms * 1e-3), 'plan': ctx.auto_plan(n)}
 
+    line = None
     if rank == 0:
         peaks, peaks_src = measured_peaks()
+        evals_per_step_rank = N * E
         value = world * evals_per_step_rank * args.steps / (ms_total * 1e-3)
         k_evals = evals_per_step_rank / (kernel_ms * 1e-3)
         achieved_tf = k_evals * FLOPS_PER_EVAL['C'] / 1e12
-        alg_bytes = N * (8.0 * case.n_params + 8.0)
+        alg_bytes = N * (8.0 * P + 8.0)
+        traffic, traffic_file = ncu_traffic()
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-            'warmup': max(args.warmup, 3), 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
+            'warmup': warm, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
             'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': dict(workload_config(world), samples_per_gpu=N),
             'clocks': clocks,
             'e2e': {'value': world * evals_per_step_rank * e2e_steps / (e2e_ms * 1e-3), 'unit': UNIT,
-                    'h2d_bytes_per_step': world * N * case.n_params * 8, 'd2h_bytes_per_step': world * N * 8,
+                    'h2d_bytes_per_step': world * N * P * 8, 'd2h_bytes_per_step': world * N * 8,
                     'ms_per_step': e2e_ms / e2e_steps, 'steps': e2e_steps,
-                    'api': 'Gaussianlikelihood.log_likelihood_batch(numpy pinned) -> stn_loglike_host',
-                    'matches_device_path': same},
+                    'api': 'Gaussianlikelihood.log_likelihood_batch(numpy pinned) -> stn_loglike_host'
+                           + (' on every rank, each rank\'s slice of the result DMA\'d into ' + assembled if world > 1 else ''),
+                    'result_assembled_in': assembled, 'matches_device_path': same, 'pageable': e2e_pageable},
             'gpu_launches': launches,
+            'gather': None if world == 1 else 'fused: the likelihood kernel\'s epilogue stores each log L into every rank\'s '
+                      '(N,) buffer over NVLink (CUDA IPC peer mappings, stn_loglike_scatter); the step ends with a '
+                      'one-element all_reduce as the barrier',
             'roofline': {
                 'bound': 'fp64', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
                 'frac': achieved_tf / peak_tf,
-                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` capture of this
-                # command (profiles/r01_ncu_loglike_fast_C.txt); algorithmic bytes per launch are alg_bytes below
-                'traffic': 744556800 + 35271424, 'traffic_unit': 'bytes per launch', 'algorithmic_bytes': alg_bytes,
-                'kernel': 'stn_loglike_fast_kernel<3,1,true>', 'kernel_ms': kernel_ms,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from one `ncu --set full` capture of this
+                # command, read from the committed summary named in traffic_source; algorithmic bytes per launch below
+                'traffic': traffic, 'traffic_unit': 'bytes per launch', 'traffic_source': traffic_file,
+                'algorithmic_bytes': alg_bytes,
+                'kernel': 'stn_loglike_fast_kernel<3,1>', 'kernel_ms': kernel_ms,
                 'flops_per_eval': FLOPS_PER_EVAL['C'],
                 'peak_source': 'stn_fp64_peak DFMA micro-benchmark in this run (MEASURED_PEAKS.json has no FP64 '
                                'figure); nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2',
@@ -344,10 +527,20 @@ def run_ours(args, rank, local_rank, world):
             'variants': variants,
             'sweep': sweep,
         }
-        print(json.dumps(line))
+        if world > 1:
+            line['sharded_bits_match'] = sharded_bits_match
+            line['strong'] = strong
+            line['single_process'] = single_process
+    if shared is not None:
+        shared.close()
+    if sharded is not None:
+        sharded.close()
     like.close()
     if world > 1:
         dist.destroy_process_group()
+    if line is not None:
+        sys.stdout.write('\n' + json.dumps(line) + '\n')      # after NCCL's teardown: the last line on stdout
+        sys.stdout.flush()
     return 0
 
 

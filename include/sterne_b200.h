@@ -34,6 +34,9 @@ enum StnRoot {
     STN_MU_D = 5, STN_OM_ASC = 6, STN_PX = 7, STN_RA = 8, STN_NROOTS = 9
 };
 
+/* Most output buffers one stn_loglike_scatter launch can write (this GPU + 7 peers). */
+#define STN_MAX_OUTS 8
+
 /* The reference's "parameter switched off" sentinel (positions.py:59). */
 #define STN_SENTINEL (-999.0)
 
@@ -146,6 +149,27 @@ int stn_destroy(StnCtx* ctx);
  * (a cudaStream_t, NULL = default stream); one stream at a time per context. */
 int stn_loglike(StnCtx* ctx, const double* theta_dev, int64_t n, int64_t ld,
                 int layout, int mode, int plan, double* out_dev, void* stream);
+
+/* stn_loglike with the result stored to n_outs buffers at once (1 <= n_outs <= STN_MAX_OUTS):
+ * outs[0] on this context's device, the others typically buffers of PEER GPUs (mapped with
+ * stn_ipc_open, or device pointers of peers with peer access enabled).  This is the multi-GPU
+ * gather of SURVEY 8(e) fused into the kernel: every GPU evaluates its slice of the batch and
+ * its epilogue stores each log L (8 bytes per vector) over NVLink directly into the slice's place
+ * in every rank's (N,) result buffer -- no collective, no second pass; the ranks only need a
+ * barrier before reading. */
+int stn_loglike_scatter(StnCtx* ctx, const double* theta_dev, int64_t n, int64_t ld,
+                        int layout, int mode, int plan, double* const* outs, int n_outs,
+                        void* stream);
+
+/* Plain device memory (cudaMalloc, so it can be exported) and CUDA IPC plumbing for the result
+ * buffers of stn_loglike_scatter when the GPUs are driven by one process each (torchrun):
+ * export a 64-byte handle, ship it to the other ranks (torch.distributed), open it there. */
+#define STN_IPC_HANDLE_BYTES 64
+int stn_dev_alloc(int device, void** ptr, int64_t bytes);
+int stn_dev_free(int device, void* ptr);
+int stn_ipc_export(void* dev_ptr, void* handle64);
+int stn_ipc_open(int device, const void* handle64, void** peer_ptr);
+int stn_ipc_close(int device, void* peer_ptr);
 
 /* Installs (copies) the prior used by stn_logpost.  Replaces: priors.create_priors_given_limits_dict
  * (priors.py:344-366) evaluated per walker by bilby. */

@@ -92,8 +92,16 @@ SYMBOLS = [
     ('stn_multi_loglike_host', _int, [_vp, _vp, _i64, _i64, _int, _int, _int, _vp]),
     ('stn_multi_loglike_dev', _int, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_i64), _i64, _int, _int, _int, _vp,
                                      _int]),
+    ('stn_loglike_scatter', _int, [_vp, _vp, _i64, _i64, _int, _int, _int, ctypes.POINTER(_vp), _int, _vp]),
+    ('stn_dev_alloc', _int, [_int, ctypes.POINTER(_vp), _i64]),
+    ('stn_dev_free', _int, [_int, _vp]),
+    ('stn_ipc_export', _int, [_vp, _vp]),
+    ('stn_ipc_open', _int, [_int, _vp, ctypes.POINTER(_vp)]),
+    ('stn_ipc_close', _int, [_int, _vp]),
 ]
 ABI_VERSION = 2
+IPC_HANDLE_BYTES = 64
+MAX_OUTS = 8
 
 
 class StnError(RuntimeError):

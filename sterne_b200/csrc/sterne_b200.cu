@@ -52,21 +52,24 @@
 #define STN_LN2       0.6931471805599453
 
 // build-time tuning knobs (defaults are the measured best; see profiles/)
-// Samples per thread for large batches.  Measured on B200 at N = 2^22 x 8 x 1024:
-// without EFAC R = 2 (128 registers, 2 CTAs/SM) wins, 30.5 vs 32.4 ms; with EFAC the longer
-// loop body prefers R = 3 (198 registers, 1 CTA/SM, no spills), 52.5 vs 56.3 ms.
+// Samples per thread for large batches (R never changes a result bit).  Measured on B200 at
+// N = 2^22 x 8 x 1024: without EFAC R = 2 (128 registers, 2 CTAs of 256 threads per SM) wins,
+// 30.5 vs 32.4 ms; with EFAC R = 3 (204 registers, no spills), 47.0 ms.
 #ifndef STN_RBIG
 #define STN_RBIG 2
 #endif
 #ifndef STN_RBIG_EFAC
 #define STN_RBIG_EFAC 3
 #endif
-// CTA shape of the R = 3 kernel: threads per CTA and CTAs per SM it is compiled for
+// CTA shape of the R >= 3 kernel.  Eight warps per SM is all 204 registers allow; as FOUR CTAs of two
+// warps (each with its own 2-stage table pipeline) instead of one CTA of eight, a warp waits at the
+// per-chunk barrier for one other warp only and the CTAs drift apart, so one CTA's prologue (sincos,
+// parameter loads) overlaps the others' epoch loops: 47.9 -> 47.0 ms (profiles/r02_kvariants.json).
 #ifndef STN_THREADS_R3
-#define STN_THREADS_R3 256
+#define STN_THREADS_R3 64
 #endif
 #ifndef STN_MINBLOCKS_R3
-#define STN_MINBLOCKS_R3 1
+#define STN_MINBLOCKS_R3 4
 #endif
 #ifndef STN_CHUNK
 #define STN_CHUNK 128
@@ -78,9 +81,12 @@
 #define STN_EFAC_UNROLL 2              /* unroll factor of the EFAC epoch loop */
 #endif
 // EFAC: exponent budget (bits) the running product of variances may drift between two
-// renormalisations; the double range is +-1022 and T stays within ~2^70 of Q.
+// renormalisations; the double range is +-1022 and T stays within 2^-100 .. 2^20 of Q.
+#ifndef STN_TAIL_SMALL_R
+#define STN_TAIL_SMALL_R 1             /* finish the last, partly filled wave of a big-R launch with the R = 1 kernel */
+#endif
 #ifndef STN_RENORM_BITS
-#define STN_RENORM_BITS 700
+#define STN_RENORM_BITS 900
 #endif
 
 namespace {
@@ -121,6 +127,8 @@ struct ProbDev {
     int n_sources, n_params, n_chunks, n_a1dot, n_sini;
     int n_prior, n_sinlim;            // n_prior = 0: likelihood only
     int out_chisq;                    // 1: write sum((res/sigma)^2) instead of log L (stn_chisq)
+    int n_extra_out;                  // stn_loglike_scatter: the result also goes to these buffers (peer GPUs)
+    double* extra_out[STN_MAX_OUTS - 1];
     double prior_const;               // sum of the priors' normalisation terms
     const int* prior_kind;
     const double* prior_a;
@@ -477,6 +485,12 @@ __device__ double prior_terms(const ProbDev& P, const double* __restrict__ theta
     return inside ? lp : -CUDART_INF;
 }
 
+// every result is stored to `out` and to the extra (typically peer-mapped) buffers of a scatter launch
+__device__ __forceinline__ void store_result(const ProbDev& P, double* __restrict__ out, int64_t n, double v) {
+    out[n] = v;
+    for (int k = 0; k < P.n_extra_out; ++k) P.extra_out[k][n] = v;
+}
+
 // ---------------------------------------------------------------------------------
 // K1: fused FAST log-likelihood
 // ---------------------------------------------------------------------------------
@@ -625,7 +639,7 @@ stn_loglike_fast_kernel(const ProbDev P, const double* __restrict__ theta, const
             const double lp = prior_terms(P, theta, nidx[r], ld, layout);
             logl[r] = (lp == -CUDART_INF) ? lp : logl[r] + lp;
         }
-        if (valid[r] && sub == 0) out[nidx[r]] = logl[r];
+        if (valid[r] && sub == 0) store_result(P, out, nidx[r], logl[r]);
     }
 }
 
@@ -643,7 +657,7 @@ stn_reduce_splits_kernel(const ProbDev P, const double* __restrict__ theta, cons
         const double lp = prior_terms(P, theta, n, ld, layout);
         logl = (lp == -CUDART_INF) ? lp : logl + lp;
     }
-    out[n] = logl;
+    store_result(P, out, n, logl);
 }
 
 // ---------------------------------------------------------------------------------
@@ -754,7 +768,7 @@ stn_loglike_strict_kernel(const ProbDev P, const double* __restrict__ theta, con
         const double lp = prior_terms(P, theta, n, ld, layout);
         logl = (lp == -CUDART_INF) ? lp : logl + lp;
     }
-    out[n] = logl;
+    store_result(P, out, n, logl);
 }
 
 // ---------------------------------------------------------------------------------
@@ -950,6 +964,7 @@ struct StnCtx {
 // Several contexts of the same problem, one per device, driven as one (stn_multi_*).
 struct StnMulti {
     std::vector<StnCtx*> ctx;
+    std::vector<int> peer_ok;           // [a * G + b]: kernels on ctx[a]'s device may store to ctx[b]'s device
 };
 
 namespace {
@@ -1071,11 +1086,14 @@ int launch_fast(StnCtx* ctx, const ProbDev& prob, const double* theta, int64_t n
 
 // scratch_slot: 0 for the device-buffer API, 1 + slot for the streams of the host pipeline
 int launch_loglike(StnCtx* ctx, const double* theta, int64_t n, int64_t ld, int layout, int mode,
-                   int plan, double* out, cudaStream_t st, int what = 0, int scratch_slot = 0) {
+                   int plan, double* out, cudaStream_t st, int what = 0, int scratch_slot = 0,
+                   double* const* extra_out = nullptr, int n_extra_out = 0) {
     // what: 0 = log L, 1 = log prior + log L, 2 = chi-square
     if (n == 0) return STN_OK;
     ProbDev prob = what == 1 ? ctx->prior_prob : ctx->prob;
     prob.out_chisq = what == 2 ? 1 : 0;
+    prob.n_extra_out = n_extra_out;
+    for (int k = 0; k < n_extra_out; ++k) prob.extra_out[k] = extra_out[k];
     if (mode == STN_MODE_STRICT) {
         STN_DBG_RANGE(theta, dbg_theta_bytes(n, ld, layout, ctx->prob.n_params), "theta");
         STN_DBG_RANGE(out, (size_t)n * sizeof(double), "out");
@@ -1120,6 +1138,27 @@ int launch_loglike(StnCtx* ctx, const double* theta, int64_t n, int64_t ld, int 
     switch (lanes) {
         case 1:
             if (R > 1) {
+                // Wave quantisation: every CTA of the big kernel runs for the same time, so a last wave
+                // that is only partly full costs a whole wave (4.6 waves at 2^19 vectors = 8 % lost).  The
+                // samples beyond the last FULL wave go to the R = 1 kernel instead: its CTAs hold a third
+                // (half) of the samples, so that tail finishes in well under one big-kernel wave.  R never
+                // changes a result bit, so this is invisible in the output.
+                const int bigR = ctx->efac_heavy ? STN_RBIG_EFAC : STN_RBIG;
+                const int64_t tile = (int64_t)threads_for(bigR) * bigR;
+                const int64_t slots = (int64_t)ctx->sm_count * minblocks_for(bigR);
+                const int64_t tiles = (n + tile - 1) / tile;
+                const int64_t n_main = (tiles / slots) * slots * tile;
+                const int64_t cap1 = (int64_t)ctx->sm_count * minblocks_for(1) * threads_for(1);
+                if (splits == 1 && n_main > 0 && n_main < n && n - n_main <= cap1 && STN_TAIL_SMALL_R) {
+                    int rc = ctx->efac_heavy
+                                 ? launch_fast<STN_RBIG_EFAC, 1>(ctx, prob, theta, n_main, ld, layout, out, st, 1, nullptr)
+                                 : launch_fast<STN_RBIG, 1>(ctx, prob, theta, n_main, ld, layout, out, st, 1, nullptr);
+                    if (rc) return rc;
+                    ProbDev tail = prob;
+                    for (int k = 0; k < tail.n_extra_out; ++k) tail.extra_out[k] += n_main;
+                    const double* th_tail = layout == STN_LAYOUT_AOS ? theta + n_main * ld : theta + n_main;
+                    return launch_fast<1, 1>(ctx, tail, th_tail, n - n_main, ld, layout, out + n_main, st, 1, nullptr);
+                }
                 if (ctx->efac_heavy) STN_GO(STN_RBIG_EFAC, 1);
                 STN_GO(STN_RBIG, 1);
             }
@@ -1175,8 +1214,32 @@ void host_pipe_drain(StnCtx* ctx) {
 }
 
 // Rows of the k-th chunk: a short first chunk (its H2D copy is the only one nothing overlaps),
-// doubling up to 2^18 rows.
-constexpr int64_t kChunkRowsMax = (int64_t)1 << 18;
+// doubling up to 2^20 rows (every chunk boundary costs a partly filled wave of CTAs).
+#ifndef STN_HOST_CHUNK_LOG2
+#define STN_HOST_CHUNK_LOG2 20
+#endif
+constexpr int64_t kChunkRowsMax = (int64_t)1 << STN_HOST_CHUNK_LOG2;
+
+// memcpy of a large block on a few threads: one core moves ~12 GB/s, which is below what the
+// kernel consumes for short-series problems and would make pageable buffers the bottleneck
+void big_memcpy(void* dst, const void* src, size_t bytes) {
+    constexpr size_t kPerThread = (size_t)8 << 20;
+    int nt = (int)(bytes / kPerThread);
+    if (nt > 4) nt = 4;
+    if (nt <= 1) {
+        std::memcpy(dst, src, bytes);
+        return;
+    }
+    const size_t part = ((bytes / nt) + 63) & ~(size_t)63;
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) {
+        const size_t lo = (size_t)t * part;
+        const size_t len = lo >= bytes ? 0 : (t == nt - 1 ? bytes - lo : part);
+        if (len) pool.emplace_back([=]() { std::memcpy((char*)dst + lo, (const char*)src + lo, len); });
+    }
+    std::memcpy(dst, src, part < bytes ? part : bytes);
+    for (std::thread& th : pool) th.join();
+}
 int64_t first_chunk_rows(int64_t n) {
     int64_t r = n / 32;
     if (r > ((int64_t)1 << 15)) r = (int64_t)1 << 15;
@@ -1266,11 +1329,11 @@ int run_host(StnCtx* ctx, const double* theta_host, int64_t n, int64_t ld, int l
                 if (k >= StnCtx::kSlots) STN_CUDA(cudaEventSynchronize(ctx->h2d_done[slot]));
                 double* hp = ctx->pin_theta[slot];
                 if (layout == STN_LAYOUT_AOS) {
-                    if (ld == P) std::memcpy(hp, theta_host + lo * ld, (size_t)m * P * sizeof(double));
+                    if (ld == P) big_memcpy(hp, theta_host + lo * ld, (size_t)m * P * sizeof(double));
                     else for (int64_t i = 0; i < m; ++i) std::memcpy(hp + i * P, theta_host + (lo + i) * ld, (size_t)P * sizeof(double));
                     src_ld = P;
                 } else {
-                    for (int c = 0; c < P; ++c) std::memcpy(hp + (int64_t)c * m, theta_host + (int64_t)c * ld + lo, (size_t)m * sizeof(double));
+                    for (int c = 0; c < P; ++c) big_memcpy(hp + (int64_t)c * m, theta_host + (int64_t)c * ld + lo, (size_t)m * sizeof(double));
                     src_ld = m;
                 }
                 src = hp;
@@ -1503,6 +1566,57 @@ int stn_loglike(StnCtx* ctx, const double* theta_dev, int64_t n, int64_t ld, int
     return launch_loglike(ctx, theta_dev, n, ld, layout, mode, plan, out_dev, static_cast<cudaStream_t>(stream));
 }
 
+int stn_loglike_scatter(StnCtx* ctx, const double* theta_dev, int64_t n, int64_t ld, int layout, int mode,
+                        int plan, double* const* outs, int n_outs, void* stream) {
+    if (!outs || n_outs < 1 || n_outs > STN_MAX_OUTS) return fail(STN_ERR_INVALID, "1..%d output buffers are needed", STN_MAX_OUTS);
+    for (int k = 0; k < n_outs; ++k)
+        if (n > 0 && !outs[k]) return fail(STN_ERR_INVALID, "null output buffer %d", k);
+    int rc = check_call(ctx, theta_dev, n, ld, layout, mode, outs[0]);
+    if (rc) return rc;
+    STN_CUDA(cudaSetDevice(ctx->device));
+    return launch_loglike(ctx, theta_dev, n, ld, layout, mode, plan, outs[0], static_cast<cudaStream_t>(stream), 0, 0,
+                          outs + 1, n_outs - 1);
+}
+
+int stn_dev_alloc(int device, void** ptr, int64_t bytes) {
+    if (!ptr || bytes < 0) return fail(STN_ERR_INVALID, "bad argument");
+    STN_CUDA(cudaSetDevice(device));
+    STN_CUDA(cudaMalloc(ptr, (size_t)(bytes ? bytes : 1)));
+    return STN_OK;
+}
+
+int stn_dev_free(int device, void* ptr) {
+    if (!ptr) return STN_OK;
+    STN_CUDA(cudaSetDevice(device));
+    STN_CUDA(cudaFree(ptr));
+    return STN_OK;
+}
+
+int stn_ipc_export(void* dev_ptr, void* handle64) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == STN_IPC_HANDLE_BYTES, "IPC handle size");
+    if (!dev_ptr || !handle64) return fail(STN_ERR_INVALID, "null argument");
+    cudaIpcMemHandle_t h;
+    STN_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
+    std::memcpy(handle64, &h, sizeof(h));
+    return STN_OK;
+}
+
+int stn_ipc_open(int device, const void* handle64, void** peer_ptr) {
+    if (!handle64 || !peer_ptr) return fail(STN_ERR_INVALID, "null argument");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, sizeof(h));
+    STN_CUDA(cudaSetDevice(device));
+    STN_CUDA(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return STN_OK;
+}
+
+int stn_ipc_close(int device, void* peer_ptr) {
+    if (!peer_ptr) return STN_OK;
+    STN_CUDA(cudaSetDevice(device));
+    STN_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+    return STN_OK;
+}
+
 int stn_set_prior(StnCtx* ctx, const StnPrior* pr) {
     if (!ctx || !pr) return fail(STN_ERR_INVALID, "null argument");
     if (pr->n_params != ctx->prob.n_params)
@@ -1641,14 +1755,20 @@ int stn_multi_create(const StnProblem* pb, const int* devices, int n_devices, St
         }
         m->ctx.push_back(c);
     }
-    // direct peer copies for stn_multi_loglike_dev (an already-enabled pair is not an error)
+    // peer access for stn_multi_loglike_dev: a kernel then stores its results straight into the
+    // gathering device's buffer over NVLink (an already-enabled pair is not an error)
+    m->peer_ok.assign((size_t)n_devices * n_devices, 0);
     for (int a = 0; a < n_devices; ++a)
         for (int b = 0; b < n_devices; ++b) {
-            if (devices[a] == devices[b]) continue;
+            if (devices[a] == devices[b]) {
+                m->peer_ok[(size_t)a * n_devices + b] = 1;
+                continue;
+            }
             int can = 0;
             if (cudaDeviceCanAccessPeer(&can, devices[a], devices[b]) == cudaSuccess && can) {
                 cudaSetDevice(devices[a]);
-                cudaDeviceEnablePeerAccess(devices[b], 0);
+                const cudaError_t e = cudaDeviceEnablePeerAccess(devices[b], 0);
+                if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) m->peer_ok[(size_t)a * n_devices + b] = 1;
             }
             (void)cudaGetLastError();
         }
@@ -1752,7 +1872,11 @@ int stn_multi_loglike_dev(StnMulti* m, const double* const* theta_dev, const int
         STN_CUDA(cudaSetDevice(c->device));
         if ((rc = host_pipe_init(c))) break;
         cudaStream_t st = c->streams[0];
-        if (c->device == out_device) {
+        bool direct = c->device == out_device;
+        for (int b = 0; b < G && !direct; ++b)
+            direct = m->ctx[b]->device == out_device && m->peer_ok[(size_t)g * G + b];
+        if (direct) {
+            // out_dev is local or peer-mapped: the kernel's own stores are the gather (8 bytes per vector over NVLink)
             rc = launch_loglike(c, theta_dev[g], cnt, ld, layout, mode, plan, out_dev + off, st, 0, 1);
         } else {
             if (c->gather_elems < cnt) {

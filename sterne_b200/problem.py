@@ -208,6 +208,13 @@ class DeviceContext(object):
     def loglike_ptr(self, theta_ptr, n, ld, layout, mode, plan, out_ptr, stream=0):
         _lib.check(self.lib.stn_loglike(self.handle, theta_ptr, n, ld, layout, mode, plan, out_ptr, stream))
 
+    def loglike_scatter_ptr(self, theta_ptr, n, ld, layout, mode, plan, out_ptrs, stream=0):
+        """stn_loglike_scatter: the result is stored to every buffer of out_ptrs (the first one on
+        this device, the others typically peer GPUs' buffers)."""
+        k = len(out_ptrs)
+        arr = (ctypes.c_void_p * k)(*[ctypes.c_void_p(int(p)) for p in out_ptrs])
+        _lib.check(self.lib.stn_loglike_scatter(self.handle, theta_ptr, n, ld, layout, mode, plan, arr, k, stream))
+
     def set_prior(self, prior):
         """prior: sampler.BoxPrior whose keys are this context's column order."""
         import numpy as np

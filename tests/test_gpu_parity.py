@@ -628,3 +628,47 @@ def test_one_process_drives_several_contexts():
         assert multi.log_likelihood() == single.log_likelihood()
         multi.close()
     single.close()
+
+
+def test_scatter_launch_writes_every_output_buffer():
+    """stn_loglike_scatter (the fused compute + gather kernel): the epilogue stores each log L to all
+    the buffers it is given -- here local ones; across GPUs they are peer mappings
+    (tests/test_nccl_multi_gpu.py).  Fast (big-R, small-R tail, split plan) and strict forms."""
+    import torch
+    case = synthetic.config5('C', n_epochs=256)
+    like = case.likelihood()
+    ctx = like._context(None)
+    dev = torch.device('cuda', 0)
+    n = 148 * 4 * 192 + 7777                       # one full wave of the R = 3 kernel + a tail for the R = 1 kernel
+    theta = synthetic.device_theta(case, n, seed=3, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    for mode, plan in ((_lib.MODE_FAST, make_plan(1)), (_lib.MODE_FAST, make_plan(1, 4)), (_lib.MODE_STRICT, 0)):
+        m = n if mode == _lib.MODE_FAST else 5000
+        want = like.log_likelihood_batch(theta[:m], plan=plan, mode=mode)
+        big = torch.full((3, n + 10), -1.0, dtype=torch.float64, device=dev)
+        outs = [big[0, 10:].data_ptr(), big[1, 5:].data_ptr(), big[2].data_ptr()]
+        ctx.loglike_scatter_ptr(theta.data_ptr(), m, case.n_params, _lib.LAYOUT_AOS, mode, plan, outs, st)
+        torch.cuda.synchronize()
+        assert torch.equal(big[0, 10:10 + m], want) and torch.equal(big[1, 5:5 + m], want) and torch.equal(big[2, :m], want)
+        assert bool((big[0, :10] == -1).all()) and bool((big[1, :5] == -1).all()) and bool((big[2, m:] == -1).all())
+    with pytest.raises(_lib.StnError):
+        ctx.loglike_scatter_ptr(theta.data_ptr(), 10, case.n_params, _lib.LAYOUT_AOS, 0, 0, [0] * 9, st)
+    like.close()
+
+
+def test_small_r_tail_is_invisible_in_the_bits():
+    """A batch whose last big-kernel wave is partly filled is finished by the R = 1 kernel; samples per
+    thread never change a bit: the same vectors evaluated alone (R = 1 throughout) give the same values."""
+    import torch
+    case = synthetic.config5('C', n_epochs=128)
+    like = case.likelihood()
+    dev = torch.device('cuda', 0)
+    n = 3 * 148 * 4 * 192 + 40000
+    theta = synthetic.device_theta(case, n, seed=17, device=dev)
+    whole = like.log_likelihood_batch(theta, plan=make_plan(1))
+    for lo, m in ((0, 1000), (148 * 4 * 192 * 3 - 500, 1000), (n - 1000, 1000)):
+        part = like.log_likelihood_batch(theta[lo:lo + m], plan=make_plan(1))       # small batch: R = 1 kernel
+        assert torch.equal(part, whole[lo:lo + m]), lo
+    soa = theta.t().contiguous()
+    assert torch.equal(like.log_likelihood_batch(soa, layout='soa', plan=make_plan(1)), whole)
+    like.close()

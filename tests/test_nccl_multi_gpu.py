@@ -1,4 +1,5 @@
-"""Hardware test of the sharded path: two ranks on two GPUs over NCCL give the single-GPU bits.
+"""Hardware test of the sharded path: ranks on separate GPUs give the single-GPU bits, both through
+the fused kernel-stores-to-peers gather (CUDA IPC + NVLink) and through the NCCL all_gather.
 Skipped on boxes with fewer than two GPUs (the CPU/gloo twin is tests/test_sharding_gloo.py)."""
 import os
 import socket
@@ -22,28 +23,41 @@ def _worker(rank, world, port, n, ret):
         case = synthetic.config5('C')
         like = case.likelihood(device=rank)
         theta = synthetic.device_theta(case, n, seed=5, device=torch.device('cuda', rank))   # same batch on each rank
-        got = ShardedLikelihood(like).log_likelihood_batch(theta)
-        ret[rank] = got.cpu().numpy()
+        sh = ShardedLikelihood(like)
+        fused = sh.log_likelihood_batch(theta)                        # kernel epilogue stores into every rank's buffer
+        again = sh.log_likelihood_batch(theta * 1.0)                  # second call: the other ping-pong buffer
+        nccl = sh.log_likelihood_batch(theta, fused=False)            # NCCL all_gather of the slices
+        lo, hi = sh.local_slice(n)
+        root_only = sh.evaluate_scatter(theta[lo:hi], n, roots=[0])   # gather to rank 0 only
+        torch.cuda.synchronize()
+        ret[rank] = (fused.cpu().numpy(), again.cpu().numpy(), nccl.cpu().numpy(),
+                     root_only.cpu().numpy() if rank == 0 else None)
+        sh.close()
         like.close()
     finally:
         dist.destroy_process_group()
 
 
-def test_two_gpu_nccl_gather_is_bit_identical_to_one_gpu():
-    if torch.cuda.device_count() < 2:
+def test_multi_gpu_gathers_are_bit_identical_to_one_gpu():
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
         pytest.skip('needs 2 GPUs')
     import torch.multiprocessing as mp
     from sterne_b200 import synthetic
+    world = min(ngpu, 8)
     n = 50001
     s = socket.socket()
     s.bind(('127.0.0.1', 0))
     port = s.getsockname()[1]
     s.close()
     ret = mp.Manager().dict()
-    mp.spawn(_worker, args=(2, port, n, ret), nprocs=2, join=True)
+    mp.spawn(_worker, args=(world, port, n, ret), nprocs=world, join=True)
     case = synthetic.config5('C')
     like = case.likelihood(device=0)
     theta = synthetic.device_theta(case, n, seed=5, device=torch.device('cuda', 0))
     want = like.log_likelihood_batch(theta, plan=like._context(None).auto_plan(n)).cpu().numpy()
     like.close()
-    assert np.array_equal(ret[0], want) and np.array_equal(ret[1], want)
+    for r in range(world):
+        fused, again, nccl, root_only = ret[r]
+        assert np.array_equal(fused, want) and np.array_equal(again, want) and np.array_equal(nccl, want), r
+    assert np.array_equal(ret[0][3], want)
