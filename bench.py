@@ -203,6 +203,11 @@ class SharedResult(object):
             return
         if rank != 0:
             self.shm = shared_memory.SharedMemory(name=name[0])
+            try:                                   # only the creating rank may unlink it (Python < 3.13 tracks attachers too)
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self.shm._name, 'shared_memory')
+            except Exception:
+                pass
         self.array = np.ndarray((n,), dtype=np.float64, buffer=self.shm.buf)
         self.pin = host_register(self.array)
         self.owner = rank == 0

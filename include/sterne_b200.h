@@ -108,6 +108,14 @@ typedef struct StnProblem {
     const int32_t* sini_col;
     const double* sini_mu;
     const double* sini_sigma;
+    /* Unit factors the reference takes from astropy.units at run time; 0 selects the library's
+     * defaults.  A host that has astropy passes astropy's own values so that the last bit agrees:
+     *   mas2rad     (u.mas).to(u.rad)        positions.py:119-120
+     *   deg2rad     (u.deg).to(u.rad)        reflex_motion.py:170 (sin / cos of Om_asc in deg)
+     *   masyr2rads  (u.mas/u.yr).to(u.rad/u.s)  kopeikin_effects.py:45 */
+    double mas2rad;
+    double deg2rad;
+    double masyr2rads;
 } StnProblem;
 
 /* Independent per-parameter priors of the reference's .inits kinds (priors.py:356-366), so a

@@ -45,6 +45,29 @@ D2S = 86400.0                          # d -> s
 YR2D = 365.25
 MASYR2RADS = MAS2RAD / (YR2D * D2S)    # (mas/yr).to(rad/s)  kopeikin_effects.py:45
 
+
+def use_astropy():
+    """The reference computes these factors with astropy at run time; when astropy is importable
+    the oracle takes astropy's own values (last-bit agreement), as sterne_b200/constants.py does."""
+    global D2YR, MAS2RAD, DEG2RAD, RAD2DEG, C_M_S, M2AU, D2S, YR2D, MASYR2RADS
+    try:
+        import astropy.units as u
+        import astropy.constants as c
+        vals = dict(D2YR=float((u.d).to(u.yr)), MAS2RAD=float((u.mas).to(u.rad)), DEG2RAD=float((u.deg).to(u.rad)),
+                    RAD2DEG=float((u.rad).to(u.deg)), C_M_S=float(c.c.to(u.m / u.s).value), M2AU=float((u.m).to(u.AU)),
+                    D2S=float((u.d).to(u.s)), YR2D=float((u.yr).to(u.d)),
+                    MASYR2RADS=float((u.mas / u.yr).to(u.rad / u.s)))
+    except Exception:
+        return False
+    g = globals()
+    if any(not (v > 0 and abs(v / g[k] - 1.0) < 1e-12) for k, v in vals.items()):
+        return False
+    g.update(vals)
+    return True
+
+
+use_astropy()
+
 ROOTS = ['dec', 'efac', 'efad', 'incl', 'mu_a', 'mu_d', 'om_asc', 'px', 'ra']
 
 

@@ -53,7 +53,10 @@ class StnProblem(ctypes.Structure):
                 ('n_sini', ctypes.c_int32),
                 ('sini_col', c_int32_p),
                 ('sini_mu', c_double_p),
-                ('sini_sigma', c_double_p)]
+                ('sini_sigma', c_double_p),
+                ('mas2rad', ctypes.c_double),
+                ('deg2rad', ctypes.c_double),
+                ('masyr2rads', ctypes.c_double)]
 
 
 # every symbol include/sterne_b200.h declares: (name, restype, argtypes)

@@ -46,6 +46,8 @@
 // ---------------------------------------------------------------------------------
 // constants (astropy unit factors; see sterne_b200/constants.py for provenance)
 // ---------------------------------------------------------------------------------
+// defaults of the three unit factors the kernels use; StnProblem may override them (the host takes
+// them from astropy.units when astropy is importable, so that the last bit matches the reference's)
 #define STN_MAS2RAD   4.84813681109536e-09          /* (pi/180)/3600*0.001 */
 #define STN_DEG2RAD   0.017453292519943295
 #define STN_MASYR2RADS (4.84813681109536e-09 / (365.25 * 86400.0))
@@ -127,6 +129,7 @@ struct ProbDev {
     int n_sources, n_params, n_chunks, n_a1dot, n_sini;
     int n_prior, n_sinlim;            // n_prior = 0: likelihood only
     int out_chisq;                    // 1: write sum((res/sigma)^2) instead of log L (stn_chisq)
+    double mas2rad, deg2rad, masyr2rads;   // unit factors (positions.py:119-120, reflex_motion.py:170, kopeikin_effects.py:45)
     int n_extra_out;                  // stn_loglike_scatter: the result also goes to these buffers (peer GPUs)
     double* extra_out[STN_MAX_OUTS - 1];
     double prior_const;               // sum of the priors' normalisation terms
@@ -243,9 +246,9 @@ struct Coef {
     double g_ra, g_dec;   // EFAC: efac^2 and (efac*efad)^2
 };
 
-__device__ __forceinline__ Coef make_coef(const SrcDev& S, const Params& p) {
+__device__ __forceinline__ Coef make_coef(const ProbDev& P, const SrcDev& S, const Params& p) {
     Coef c;
-    const double K = STN_MAS2RAD;
+    const double K = P.mas2rad;
     double sd, cd, sa, ca;
     sincos(p.dec, &sd, &cd);
     sincos(p.ra, &sa, &ca);
@@ -265,7 +268,7 @@ __device__ __forceinline__ Coef make_coef(const SrcDev& S, const Params& p) {
                        (p.om_asc != STN_SENTINEL);        // positions.py:117
     if (rf_on) {
         double sO, cO;
-        sincos(p.om_asc * STN_DEG2RAD, &sO, &cO);
+        sincos(p.om_asc * P.deg2rad, &sO, &cO);
         const double ci = cos(p.incl);
         const double pk = pxe * K;
         c.r0c = pk * sO * S.inv_cos_decj;
@@ -446,8 +449,8 @@ __device__ double constraint_terms(const ProbDev& P, const double* __restrict__ 
             const double om = load_param(theta, n, S.col[STN_OM_ASC], ld, layout);
             const double mu = sqrt(mu_a * mu_a + mu_d * mu_d);
             const double th = atan2(mu_a, mu_d);
-            double v = mu * sin(th - om * STN_DEG2RAD) / tan(inc);
-            v = (v * S.a1_lts) * STN_MASYR2RADS;
+            double v = mu * sin(th - om * P.deg2rad) / tan(inc);
+            v = (v * S.a1_lts) * P.masyr2rads;
             const double z = (v - P.a1_mu[k]) / P.a1_sigma[k];
             s += z * z;
         }
@@ -575,7 +578,7 @@ stn_loglike_fast_kernel(const ProbDev P, const double* __restrict__ theta, const
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const Params p = load_params(S, theta, nidx[r], ld, layout);
-                cf[r] = make_coef(S, p);
+                cf[r] = make_coef(P, S, p);
                 acc[r].chi_ra = 0.0;
                 acc[r].chi_dec = 0.0;
                 acc[r].prod = 1.0;
@@ -669,7 +672,7 @@ struct StrictTrig {
     bool px_on, rf_on;
 };
 
-__device__ __forceinline__ StrictTrig strict_trig(const SrcDev& S, const Params& p) {
+__device__ __forceinline__ StrictTrig strict_trig(const ProbDev& P, const SrcDev& S, const Params& p) {
     StrictTrig t;
     t.sd = sin(p.dec);
     t.cd = cos(p.dec);
@@ -679,7 +682,7 @@ __device__ __forceinline__ StrictTrig strict_trig(const SrcDev& S, const Params&
     t.rf_on = t.px_on && S.binary && (p.incl != STN_SENTINEL) && (p.om_asc != STN_SENTINEL);
     t.sO = t.cO = t.ci = 0.0;
     if (t.rf_on) {
-        const double Om = __dmul_rn(p.om_asc, STN_DEG2RAD);
+        const double Om = __dmul_rn(p.om_asc, P.deg2rad);
         t.sO = sin(Om);
         t.cO = cos(Om);
         t.ci = cos(p.incl);
@@ -723,7 +726,7 @@ stn_loglike_strict_kernel(const ProbDev P, const double* __restrict__ theta, con
     for (int s = 0; s < P.n_sources; ++s) {
         const SrcDev& S = P.src[s];
         const Params p = load_params(S, theta, n, ld, layout);
-        const StrictTrig t = strict_trig(S, p);
+        const StrictTrig t = strict_trig(P, S, p);
         const bool ef_on = S.efac_on && (p.efac != STN_SENTINEL);
         const double efad = (p.efad != STN_SENTINEL) ? p.efad : 1.0;
         double chi = 0.0, slog = 0.0;
@@ -735,7 +738,7 @@ stn_loglike_strict_kernel(const ProbDev P, const double* __restrict__ theta, con
                 strict_offsets(S, p, t, row, ora, odec);
                 const double ref = half == 0 ? p.ra : p.dec;
                 const double off = half == 0 ? ora : odec;
-                const double model = __dadd_rn(ref, __dmul_rn(off, STN_MAS2RAD));
+                const double model = __dadd_rn(ref, __dmul_rn(off, P.mas2rad));
                 const double res = __dsub_rn(row[4 + half], model);
                 double err;
                 if (S.efac_on) {
@@ -788,19 +791,19 @@ stn_model_kernel(const ProbDev P, const int source, const double* __restrict__ t
     const Params p = load_params(S, theta, n, ld, layout);
     double m_ra, m_dec, o_ra, o_dec;
     if (mode == STN_MODE_STRICT) {
-        const StrictTrig t = strict_trig(S, p);
+        const StrictTrig t = strict_trig(P, S, p);
         strict_offsets(S, p, t, S.strict_rows + (int64_t)e * STN_STRICT_ROW, o_ra, o_dec);
-        m_ra = __dadd_rn(p.ra, __dmul_rn(o_ra, STN_MAS2RAD));
-        m_dec = __dadd_rn(p.dec, __dmul_rn(o_dec, STN_MAS2RAD));
+        m_ra = __dadd_rn(p.ra, __dmul_rn(o_ra, P.mas2rad));
+        m_dec = __dadd_rn(p.dec, __dmul_rn(o_dec, P.mas2rad));
     } else {
-        const Coef c = make_coef(S, p);
+        const Coef c = make_coef(P, S, p);
         const double2* row = reinterpret_cast<const double2*>(S.fast_rows + (int64_t)e * STN_FAST_ROW);
         double ok_ra, ok_dec;
         fast_offsets<true>(c, row[0], row[1], row[5], ok_ra, ok_dec);
         m_ra = c.ra + ok_ra;
         m_dec = c.dec + ok_dec;
-        o_ra = ok_ra / STN_MAS2RAD;
-        o_dec = ok_dec / STN_MAS2RAD;
+        o_ra = ok_ra / P.mas2rad;
+        o_dec = ok_dec / P.mas2rad;
     }
     double* rd = radec + n * (2 * (int64_t)E);
     rd[e] = m_ra;
@@ -1514,6 +1517,9 @@ int stn_create(const StnProblem* pb, int device, StnCtx** out_ctx) {
     P.n_chunks = (int)chunks.size();
     P.n_a1dot = pb->n_a1dot;
     P.n_sini = pb->n_sini;
+    P.mas2rad = pb->mas2rad > 0.0 ? pb->mas2rad : STN_MAS2RAD;
+    P.deg2rad = pb->deg2rad > 0.0 ? pb->deg2rad : STN_DEG2RAD;
+    P.masyr2rads = pb->masyr2rads > 0.0 ? pb->masyr2rads : STN_MASYR2RADS;
     int rc;
     if ((rc = upload(ctx, src.data(), src.size(), &P.src))) return bail(rc);
     if ((rc = upload(ctx, chunks.data(), chunks.size(), &P.chunks))) return bail(rc);

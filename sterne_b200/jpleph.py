@@ -9,10 +9,14 @@ with one vectorised evaluation for all epochs, so that neither novas nor TEMPO2'
 needed -- only the ephemeris file.
 
 STATUS: the image holds no JPL ephemeris file, so this reader is validated against files
-written by `write_jpl_file` below (same layout, Chebyshev coefficients fitted to a known
-orbit) -- record addressing, sub-interval selection, Chebyshev evaluation, byte order and
-the Earth = EMB - Moon/(1 + EMRAT) combination are tested; agreement with a real DE421 file
-is NOT verified here.
+written by `write_jpl_file` below (Chebyshev coefficients fitted to a known orbit), both in a
+minimal two-body layout and in DE405 / DE421's REAL record layout -- the published GROUP 1050
+pointer table with all 13 items, NCOEFF = 1018 doubles per record, 32-day records starting at
+JD 2433264.5, Earth-Moon barycentre at offset 231 (13 coefficients x 2 sub-intervals), Moon at
+441 (13 x 8), every other body's slots filled with a poison value -- in both byte orders.
+Record addressing at the real offsets, sub-interval selection, Chebyshev evaluation, byte
+order and the Earth = EMB - Moon/(1 + EMRAT) combination are tested that way.  Agreement with
+a REAL `DE421.1950.2050` file remains UNVERIFIED: none exists in this image or on the GPU boxes.
 
 File layout (JPL export format; every record is NCOEFF doubles):
   record 0  title 3x84 bytes | constant names 400x6 bytes | SS[3] = start JD, end JD, days per record
@@ -99,20 +103,40 @@ class JPLEphemerisProvider(object):
         return (emb - moon / (1.0 + self.emrat)) / self.au_km
 
 
+# GROUP 1050 of the DE405 / DE421 headers: (offset, coefficients per component, sub-intervals) of
+# Mercury, Venus, EMB, Mars, Jupiter, Saturn, Uranus, Neptune, Pluto, Moon, Sun, nutations, librations
+DE421_GROUP_1050 = [(3, 14, 4), (171, 10, 2), (231, 13, 2), (309, 11, 1), (342, 8, 1), (366, 7, 1), (387, 6, 1),
+                    (405, 6, 1), (423, 6, 1), (441, 13, 8), (753, 11, 2), (819, 10, 4), (899, 10, 4)]
+DE421_NCOEFF = 1018
+DE421_JD_START, DE421_JD_END = 2433264.5, 2469808.5
+
+
 def write_jpl_file(path, emb_km, moon_km, jd_start, jd_end, step=32.0, ncf=(13, 13), na=(2, 8), au_km=149597870.7,
-                   emrat=81.30056, denum=421, byteorder='<'):
-    """Writes a JPL export-format file holding only the Earth-Moon barycentre and the geocentric
+                   emrat=81.30056, denum=421, byteorder='<', layout='minimal', poison=1.0e30):
+    """Writes a JPL export-format file holding the Earth-Moon barycentre and the geocentric
     Moon, Chebyshev-fitted to the callables emb_km(jd[M]) / moon_km(jd[M]) -> (M, 3) km.
+    layout='minimal': only those two bodies.  layout='de421': DE405 / DE421's real record layout
+    (DE421_GROUP_1050, 1018 doubles per record; ncf / na are ignored), the slots of every other
+    body filled with `poison` so that a wrong offset cannot go unnoticed.
     For tests and for exporting other ephemerides into the format this package reads."""
     from numpy.polynomial import chebyshev as C
-    ipt = [(3, 0, 0)] * 12
-    off = 3
-    ipt[_EMB] = (off, ncf[0], na[0])
-    off += 3 * ncf[0] * na[0]
-    ipt[_MOON] = (off, ncf[1], na[1])
-    off += 3 * ncf[1] * na[1]
-    ipt = [(off, 0, 0) if p[1] == 0 else p for p in ipt]
-    ncoeff = off - 1
+    if layout == 'de421':
+        ipt = list(DE421_GROUP_1050[:12])
+        lpt = DE421_GROUP_1050[12]
+        ncoeff = DE421_NCOEFF
+        off = lpt[0]
+    elif layout == 'minimal':
+        ipt = [(3, 0, 0)] * 12
+        off = 3
+        ipt[_EMB] = (off, ncf[0], na[0])
+        off += 3 * ncf[0] * na[0]
+        ipt[_MOON] = (off, ncf[1], na[1])
+        off += 3 * ncf[1] * na[1]
+        ipt = [(off, 0, 0) if p[1] == 0 else p for p in ipt]
+        lpt = (off, 0, 0)
+        ncoeff = off - 1
+    else:
+        raise ValueError('layout must be "minimal" or "de421"')
     nrec = int(round((jd_end - jd_start) / step))
     o = byteorder
     header = bytearray(8 * ncoeff)
@@ -122,10 +146,10 @@ def write_jpl_file(path, emb_km, moon_km, jd_start, jd_end, step=32.0, ncf=(13, 
     struct.pack_into(o + '2d', header, _NAMES_END + 28, au_km, emrat)
     struct.pack_into(o + '36i', header, _NAMES_END + 44, *[v for p in ipt for v in p])
     struct.pack_into(o + 'i', header, _NAMES_END + 188, denum)
-    struct.pack_into(o + '3i', header, _NAMES_END + 192, off, 0, 0)
+    struct.pack_into(o + '3i', header, _NAMES_END + 192, *lpt)
     if 8 * ncoeff < _NAMES_END + 204:
         raise ValueError('records too short to hold the header: use more coefficients')
-    recs = np.zeros((nrec, ncoeff))
+    recs = np.full((nrec, ncoeff), poison if layout == 'de421' else 0.0)
     for r in range(nrec):
         t0 = jd_start + r * step
         recs[r, 0], recs[r, 1] = t0, t0 + step

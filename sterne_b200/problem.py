@@ -7,7 +7,7 @@ Everything here is parameter-independent and runs once per problem on the host.
 import ctypes
 import numpy as np
 
-from . import _lib
+from . import _lib, constants
 from .constants import ROOTS, D2YR, DEG2RAD, C_M_S
 from .ephemeris import earth_vectors
 from .orbit import orbit_terms
@@ -171,6 +171,8 @@ class CompiledProblem(object):
         pb.sini_col = self.sini_col.ctypes.data_as(_lib.c_int32_p)
         pb.sini_mu = self.sini_mu.ctypes.data_as(_lib.c_double_p)
         pb.sini_sigma = self.sini_sigma.ctypes.data_as(_lib.c_double_p)
+        # the factors this host resolved (astropy's own when astropy is importable, constants.py)
+        pb.mas2rad, pb.deg2rad, pb.masyr2rads = constants.MAS2RAD, constants.DEG2RAD, constants.MASYR2RADS
         return pb, (arr, self)
 
     @property

@@ -175,3 +175,51 @@ def test_parfile_substring_quirks_match_reference(golden, tmp_path):
     assert sb.read_parfile(str(p)) == q['ref']
     assert O.read_parfile(str(p)) == q['ref']
     assert q['ref']['ecc'] == 1.5e-15 and q['ref']['om'] == 45.0
+
+
+def test_unit_factors_are_injectable(monkeypatch):
+    """The reference takes its unit factors from astropy at run time; this package takes astropy's own
+    values when astropy is importable and hands them to the library (StnProblem.mas2rad ...).  No astropy
+    exists here, so a stand-in whose mas->rad is the OTHER candidate double (pi/648000000, 1 ulp from the
+    built-in (pi/180)/3600*0.001) is injected."""
+    import math
+    import types
+    from sterne_b200 import constants, problem
+    other = math.pi / 648000000.0
+    assert other != constants.MAS2RAD and abs(other / constants.MAS2RAD - 1) < 1e-15
+
+    class Unit(object):
+        def __init__(self, name, scale):
+            self.name, self.scale = name, scale
+
+        def to(self, target):
+            table = {('d', 'yr'): constants.D2YR, ('mas', 'rad'): other, ('deg', 'rad'): constants.DEG2RAD,
+                     ('rad', 'deg'): constants.RAD2DEG, ('AU', 'm'): constants.AU_M, ('m', 'AU'): constants.M2AU,
+                     ('d', 's'): constants.D2S, ('yr', 'd'): constants.YR2D,
+                     ('mas/yr', 'rad/s'): other / (constants.YR2D * constants.D2S), ('c', 'm/s'): constants.C_M_S}
+            v = table[(self.name, target.name)]
+            return types.SimpleNamespace(value=v) if self.name == 'c' else v
+
+        def __truediv__(self, o):
+            return Unit(self.name + '/' + o.name, None)
+
+    u = types.SimpleNamespace(__name__='fake_units', **{n: Unit(n, None) for n in ('d', 'yr', 'mas', 'rad', 'deg', 'AU', 'm', 's')})
+    c = types.SimpleNamespace(c=Unit('c', None))
+    saved = {k: getattr(constants, k) for k in ('D2YR', 'MAS2RAD', 'DEG2RAD', 'RAD2DEG', 'C_M_S', 'AU_M', 'M2AU', 'D2S',
+                                                'YR2D', 'MASYR2RADS', 'SOURCE')}
+    try:
+        assert constants.use_astropy(u, c)
+        assert constants.MAS2RAD == other and constants.SOURCE == 'injected'
+        case = synthetic.config1()
+        pb, keep = problem.CompiledProblem(case.refepoch, case.LoD_timing, case.LoD_VLBI, case.shares,
+                                           earth_xyz=case.earth_xyz).as_ctypes()
+        assert pb.mas2rad == other and pb.deg2rad == constants.DEG2RAD
+        assert pb.masyr2rads == other / (constants.YR2D * constants.D2S)
+    finally:
+        for k, v in saved.items():
+            setattr(constants, k, v)
+    # a factor that is off by more than rounding (a broken or foreign 'astropy') is refused
+    bad = types.SimpleNamespace(__name__='fake_units', **{n: Unit(n, None) for n in ('d', 'yr', 'mas', 'rad', 'deg', 'AU', 'm', 's')})
+    bad.mas = types.SimpleNamespace(name='mas', to=lambda t: 1.0, __truediv__=None)
+    assert not constants.use_astropy(bad, c)
+    assert constants.MAS2RAD == saved['MAS2RAD']

@@ -74,3 +74,29 @@ def test_rejects_non_ephemeris_files(tmp_path):
     p.write_bytes(b'\0' * 10000)
     with pytest.raises(ValueError):
         JPLEphemerisProvider(str(p))
+
+
+@pytest.mark.parametrize('order', ['<', '>'])
+def test_real_de421_record_layout(order, tmp_path):
+    """The published DE405 / DE421 GROUP 1050 table: 13 items, NCOEFF 1018, 32-day records from
+    JD 2433264.5, EMB at offset 231 (13 x 2), Moon at 441 (13 x 8); all other bodies poisoned."""
+    from sterne_b200.jpleph import DE421_GROUP_1050, DE421_NCOEFF, DE421_JD_START
+    path = str(tmp_path / 'DE421.layout')
+    n_rec = 24
+    ncoeff = write_jpl_file(path, _emb_km, _moon_km, DE421_JD_START, DE421_JD_START + 32.0 * n_rec, byteorder=order,
+                            layout='de421')
+    assert ncoeff == DE421_NCOEFF == 1018
+    assert os.path.getsize(path) == (2 + n_rec) * 1018 * 8
+    prov = JPLEphemerisProvider(path)
+    assert prov.order == order and prov.ncoeff == 1018 and prov.denum == 421
+    assert prov.ipt == DE421_GROUP_1050
+    assert prov.ipt[2] == (231, 13, 2) and prov.ipt[9] == (441, 13, 8) and prov.ipt[12] == (899, 10, 4)
+    assert prov.ss == (DE421_JD_START, DE421_JD_START + 32.0 * n_rec, 32.0)
+    rng = np.random.default_rng(1)
+    jd = np.concatenate([DE421_JD_START + rng.uniform(0, 32.0 * n_rec, 2000),
+                         DE421_JD_START + np.array([0.0, 16.0, 4.0, 32.0, 32.0 * n_rec, 32.0 * n_rec - 1e-9])])
+    got = prov(jd)
+    want = (_emb_km(jd) - _moon_km(jd) / (1 + EMRAT)) / AU_KM
+    assert np.abs(got - want).max() < 2e-11          # a read from any other body's slots would return ~1e30 / AU
+    # MJD 33282.0 = JD 2433282.5 is the first epoch of the file name's "1950" (1950-01-01); it lies in record 0
+    assert np.abs(prov(np.array([2433282.5])) - (_emb_km(np.array([2433282.5])) - _moon_km(np.array([2433282.5])) / (1 + EMRAT)) / AU_KM).max() < 2e-11
