@@ -267,6 +267,21 @@ int stn_stretch_accept(int device, double* x_dev, double* lp_dev, int64_t n_walk
                        int64_t ld, int half, uint64_t seed, uint64_t step, const double* y_dev,
                        const double* z_dev, const double* lpy_dev, int64_t* n_accept_dev, void* stream);
 
+/* n_steps full ensemble steps (both halves) of the stretch move on device-resident walkers in ONE call;
+ * requires stn_set_prior.  x_dev (W, ld >= P) and lp_dev (W) are updated in place (lp_dev must hold the
+ * walkers' current log-posteriors, e.g. from stn_logpost); every `thin`-th state is copied to chain_dev
+ * ((n_steps / thin, W, P), nullable) and lnprob_dev ((n_steps / thin, W), nullable); acceptances are added
+ * to *n_accept_dev.  Random numbers and arithmetic are those of stn_stretch_propose / stn_logpost /
+ * stn_stretch_accept with step counters step0, step0 + 1, ...: the chain does not depend on the engine.
+ * engine 0 chooses: short series (<= 512 epochs over all sources; the reference's real-data regime,
+ * simulate.py:191-192 with ~10 epochs per source) run as ONE persistent cooperative kernel with the
+ * likelihood evaluated inline and a grid-wide barrier between half-steps (no launch per step at all);
+ * long series use the throughput kernel, three launches per half-step issued from this call.
+ * engine 1 / 2 force the persistent kernel / the launch loop.  Asynchronous on `stream`. */
+int stn_ensemble_run(StnCtx* ctx, double* x_dev, double* lp_dev, int64_t n_walkers, int64_t ld, double a,
+                     uint64_t seed, uint64_t step0, int64_t n_steps, int64_t thin, double* chain_dev,
+                     double* lnprob_dev, int64_t* n_accept_dev, int mode, int plan, int engine, void* stream);
+
 /* Timing helper for bench.py: runs `steps` back-to-back stn_loglike launches on an
  * internal stream bracketed by CUDA events on that stream; returns total ms. */
 int stn_loglike_timed(StnCtx* ctx, const double* theta_dev, int64_t n, int64_t ld,

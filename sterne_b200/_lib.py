@@ -101,6 +101,8 @@ SYMBOLS = [
     ('stn_ipc_export', _int, [_vp, _vp]),
     ('stn_ipc_open', _int, [_int, _vp, ctypes.POINTER(_vp)]),
     ('stn_ipc_close', _int, [_int, _vp]),
+    ('stn_ensemble_run', _int, [_vp, _vp, _vp, _i64, _i64, ctypes.c_double, ctypes.c_uint64, ctypes.c_uint64, _i64, _i64,
+                                _vp, _vp, _vp, _int, _int, _int, _vp]),
 ]
 ABI_VERSION = 2
 IPC_HANDLE_BYTES = 64

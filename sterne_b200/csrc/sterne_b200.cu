@@ -22,6 +22,7 @@
 #include "sterne_b200.h"
 
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <math_constants.h>
 // -DSTN_DEBUG (python -m sterne_b200.build --debug): device-side asserts on every index the kernels
 // form, and host-side checks that every device buffer a launch is given (the caller's and the
@@ -84,6 +85,9 @@
 #endif
 // EFAC: exponent budget (bits) the running product of variances may drift between two
 // renormalisations; the double range is +-1022 and T stays within 2^-100 .. 2^20 of Q.
+#ifndef STN_SAMPLER_CLUSTER
+#define STN_SAMPLER_CLUSTER 1          /* fused sampler: one thread-block cluster + hardware barrier when <= 16 CTAs */
+#endif
 #ifndef STN_TAIL_SMALL_R
 #define STN_TAIL_SMALL_R 1             /* finish the last, partly filled wave of a big-R launch with the R = 1 kernel */
 #endif
@@ -204,30 +208,35 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // ---------------------------------------------------------------------------------
 // parameter fetch (routing table resolved on the host: positions.py:32-60)
 // ---------------------------------------------------------------------------------
+// COH: plain (coherent, generic-address) loads instead of the read-only path -- for parameter vectors that
+// the running kernel itself has written (the fused sampler's proposals, which may live in local memory)
+template <bool COH = false>
 __device__ __forceinline__ double load_param(const double* __restrict__ theta, int64_t n, int col,
                                              int64_t ld, int layout) {
     if (col < 0) return STN_SENTINEL;
     STN_ASSERT(n >= 0 && (layout == STN_LAYOUT_SOA ? n < ld : col < ld));
-    return layout == STN_LAYOUT_SOA ? __ldg(theta + (int64_t)col * ld + n)
-                                    : __ldg(theta + n * ld + col);
+    const double* p = layout == STN_LAYOUT_SOA ? theta + (int64_t)col * ld + n : theta + n * ld + col;
+    if (COH) return *reinterpret_cast<const volatile double*>(p);
+    return __ldg(p);
 }
 
 struct Params {
     double dec, efac, efad, incl, mu_a, mu_d, om_asc, px, ra;
 };
 
+template <bool COH = false>
 __device__ __forceinline__ Params load_params(const SrcDev& S, const double* __restrict__ theta,
                                               int64_t n, int64_t ld, int layout) {
     Params p;
-    p.dec = load_param(theta, n, S.col[STN_DEC], ld, layout);
-    p.efac = load_param(theta, n, S.col[STN_EFAC], ld, layout);
-    p.efad = load_param(theta, n, S.col[STN_EFAD], ld, layout);
-    p.incl = load_param(theta, n, S.col[STN_INCL], ld, layout);
-    p.mu_a = load_param(theta, n, S.col[STN_MU_A], ld, layout);
-    p.mu_d = load_param(theta, n, S.col[STN_MU_D], ld, layout);
-    p.om_asc = load_param(theta, n, S.col[STN_OM_ASC], ld, layout);
-    p.px = load_param(theta, n, S.col[STN_PX], ld, layout);
-    p.ra = load_param(theta, n, S.col[STN_RA], ld, layout);
+    p.dec = load_param<COH>(theta, n, S.col[STN_DEC], ld, layout);
+    p.efac = load_param<COH>(theta, n, S.col[STN_EFAC], ld, layout);
+    p.efad = load_param<COH>(theta, n, S.col[STN_EFAD], ld, layout);
+    p.incl = load_param<COH>(theta, n, S.col[STN_INCL], ld, layout);
+    p.mu_a = load_param<COH>(theta, n, S.col[STN_MU_A], ld, layout);
+    p.mu_d = load_param<COH>(theta, n, S.col[STN_MU_D], ld, layout);
+    p.om_asc = load_param<COH>(theta, n, S.col[STN_OM_ASC], ld, layout);
+    p.px = load_param<COH>(theta, n, S.col[STN_PX], ld, layout);
+    p.ra = load_param<COH>(theta, n, S.col[STN_RA], ld, layout);
     return p;
 }
 
@@ -436,6 +445,7 @@ __device__ __forceinline__ double group_sum(double v) {
 }
 
 // a1dot (kopeikin_effects.py:41-45) and sin(incl) (simulate.py:379-383) Gaussian terms
+template <bool COH = false>
 __device__ double constraint_terms(const ProbDev& P, const double* __restrict__ theta, int64_t n,
                                    int64_t ld, int layout) {
     double add = 0.0;
@@ -443,10 +453,10 @@ __device__ double constraint_terms(const ProbDev& P, const double* __restrict__ 
         double s = 0.0;
         for (int k = 0; k < P.n_a1dot; ++k) {
             const SrcDev& S = P.src[P.a1_src[k]];
-            const double inc = load_param(theta, n, S.col[STN_INCL], ld, layout);
-            const double mu_a = load_param(theta, n, S.col[STN_MU_A], ld, layout);
-            const double mu_d = load_param(theta, n, S.col[STN_MU_D], ld, layout);
-            const double om = load_param(theta, n, S.col[STN_OM_ASC], ld, layout);
+            const double inc = load_param<COH>(theta, n, S.col[STN_INCL], ld, layout);
+            const double mu_a = load_param<COH>(theta, n, S.col[STN_MU_A], ld, layout);
+            const double mu_d = load_param<COH>(theta, n, S.col[STN_MU_D], ld, layout);
+            const double om = load_param<COH>(theta, n, S.col[STN_OM_ASC], ld, layout);
             const double mu = sqrt(mu_a * mu_a + mu_d * mu_d);
             const double th = atan2(mu_a, mu_d);
             double v = mu * sin(th - om * P.deg2rad) / tan(inc);
@@ -457,7 +467,7 @@ __device__ double constraint_terms(const ProbDev& P, const double* __restrict__ 
         add += -0.5 * s;
     }
     for (int k = 0; k < P.n_sini; ++k) {
-        const double x = load_param(theta, n, P.sini_col[k], ld, layout);
+        const double x = load_param<COH>(theta, n, P.sini_col[k], ld, layout);
         const double z = (P.sini_mu[k] - sin(x)) / P.sini_sigma[k];
         add += -0.5 * (z * z);
     }
@@ -465,12 +475,13 @@ __device__ double constraint_terms(const ProbDev& P, const double* __restrict__ 
 }
 
 // log prior of one parameter vector (priors.py:356-366; -inf outside the support)
+template <bool COH = false>
 __device__ double prior_terms(const ProbDev& P, const double* __restrict__ theta, int64_t n, int64_t ld,
                               int layout) {
     double lp = P.prior_const;
     bool inside = true;
     for (int k = 0; k < P.n_prior; ++k) {
-        const double x = load_param(theta, n, k, ld, layout);
+        const double x = load_param<COH>(theta, n, k, ld, layout);
         const double a = P.prior_a[k], b = P.prior_b[k];
         const int kind = P.prior_kind[k];
         if (kind == STN_PRIOR_GAUSSIAN) {
@@ -482,10 +493,83 @@ __device__ double prior_terms(const ProbDev& P, const double* __restrict__ theta
         }
     }
     for (int k = 0; k < P.n_sinlim; ++k) {
-        const double sx = sin(load_param(theta, n, P.sinlim_col[k], ld, layout));
+        const double sx = sin(load_param<COH>(theta, n, P.sinlim_col[k], ld, layout));
         inside = inside && (sx >= P.sinlim_lo[k]) && (sx <= P.sinlim_hi[k]);
     }
     return inside ? lp : -CUDART_INF;
+}
+
+// ---------------------------------------------------------------------------------
+// Per-source building blocks shared by K1 and the fused sampler kernel: begin (parameters ->
+// coefficients, empty sums), chunk (epoch loop over one chunk of the table), fold (sums -> log L).
+// ---------------------------------------------------------------------------------
+template <int R>
+struct SrcState {
+    Coef cf[R];
+    Acc acc[R];
+    int mask;     // EFAC: epochs between two renormalisations, minus one (warp-uniform)
+    int nvar;     // EFAC: epochs this lane has folded into Q since src_begin
+};
+
+template <int R, bool COH>
+__device__ __forceinline__ void src_begin(const ProbDev& P, const SrcDev& S, const double* __restrict__ theta,
+                                          const int64_t (&nidx)[R], int64_t ld, int layout, SrcState<R>& st) {
+    const bool ef = S.efac_on != 0;
+    int m = kChunk - 1;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const Params p = load_params<COH>(S, theta, nidx[r], ld, layout);
+        st.cf[r] = make_coef(P, S, p);
+        st.acc[r].chi_ra = 0.0;
+        st.acc[r].chi_dec = 0.0;
+        st.acc[r].prod = 1.0;
+        st.acc[r].esum = 0;
+        if (ef) m = min(m, renorm_mask(S, st.cf[r]));
+    }
+    // the cadence only has to be uniform over the warp (the epoch loops stay converged); it
+    // never changes a bit of the result
+    st.mask = ef ? __reduce_min_sync(0xffffffffu, m) : m;
+    st.nvar = 0;
+}
+
+template <int R, int L>
+__device__ __forceinline__ void src_chunk(const SrcDev& S, const double* __restrict__ rows, int n_epochs, int sub,
+                                          SrcState<R>& st) {
+    const bool ef = S.efac_on != 0;
+    const bool bin = S.binary != 0;
+    if (!ef && !bin) epoch_loop<R, L, false, false>(rows, n_epochs, sub, st.cf, st.acc, st.mask);
+    else if (!ef && bin) epoch_loop<R, L, false, true>(rows, n_epochs, sub, st.cf, st.acc, st.mask);
+    else if (ef && !bin) epoch_loop<R, L, true, false>(rows, n_epochs, sub, st.cf, st.acc, st.mask);
+    else epoch_loop<R, L, true, true>(rows, n_epochs, sub, st.cf, st.acc, st.mask);
+    if (ef) st.nvar += sub < n_epochs ? (n_epochs - sub + L - 1) / L : 0;
+}
+
+// log_p += -0.5*sum((res/errs)^2); log_p += -sum(log(errs))  (simulate.py:370-371)
+template <int R, int L>
+__device__ __forceinline__ void src_fold(const ProbDev& P, const SrcDev& S, bool source_ends, SrcState<R>& st,
+                                         double (&logl)[R]) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        double chi, logdet;
+        if (S.efac_on) {
+            // chi^2 = 2^k T / Q;  -sum(log sigma) = -0.5 log(prod of variances), the table's
+            // variances being stored times 2^k (two per epoch)
+            renorm(st.acc[r]);                                   // Q into [1, 2): log() sees the same bits
+            chi = group_sum<L>((st.acc[r].chi_ra / st.acc[r].prod) * S.chi_scale);
+            const double part = log(st.acc[r].prod) + (double)(st.acc[r].esum - 2 * st.nvar * S.v_shift) * STN_LN2;
+            logdet = -0.5 * group_sum<L>(part);
+        } else {
+            chi = group_sum<L>(st.acc[r].chi_ra + st.acc[r].chi_dec);
+            // host constant, counted once: by the split that holds the source's last chunk
+            logdet = source_ends ? S.neg_sum_log_err : 0.0;
+        }
+        if (P.out_chisq) {
+            logl[r] += chi;
+        } else {
+            logl[r] += -0.5 * chi;
+            logl[r] += logdet;
+        }
+    }
 }
 
 // every result is stored to `out` and to the extra (typically peer-mapped) buffers of a scatter launch
@@ -547,10 +631,9 @@ stn_loglike_fast_kernel(const ProbDev P, const double* __restrict__ theta, const
     }
 
     double logl[R];
-    Coef cf[R];
-    Acc acc[R];
-    int mask = kChunk - 1;        // EFAC: epochs between two renormalisations, minus one (warp-uniform)
-    int nvar = 0;                 // EFAC: epochs this lane has folded into Q since `first`
+    SrcState<R> st;
+    st.mask = kChunk - 1;
+    st.nvar = 0;
 #pragma unroll
     for (int r = 0; r < R; ++r) logl[r] = 0.0;
 
@@ -571,58 +654,10 @@ stn_loglike_fast_kernel(const ProbDev P, const double* __restrict__ theta, const
         const SrcDev& S = P.src[ck.source];
         const bool first = (ck.flags & kFirst) || c == c_begin;   // (re)start this source's sums
         const bool last = (ck.flags & kLast) || c == c_end - 1;   // fold them into log L
-        const bool ef = S.efac_on != 0;
-        const bool bin = S.binary != 0;
-        if (first) {
-            int m = kChunk - 1;
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const Params p = load_params(S, theta, nidx[r], ld, layout);
-                cf[r] = make_coef(P, S, p);
-                acc[r].chi_ra = 0.0;
-                acc[r].chi_dec = 0.0;
-                acc[r].prod = 1.0;
-                acc[r].esum = 0;
-                if (ef) m = min(m, renorm_mask(S, cf[r]));
-            }
-            // the cadence only has to be uniform over the warp (the epoch loops stay converged); it
-            // never changes a bit of the result
-            mask = ef ? __reduce_min_sync(0xffffffffu, m) : m;
-            nvar = 0;
-        }
+        if (first) src_begin<R, false>(P, S, theta, nidx, ld, layout, st);
         mbar_wait(&full[it & 1], (uint32_t)((it >> 1) & 1));
-        const double* rows = stage[it & 1];
-        if (!ef && !bin) epoch_loop<R, L, false, false>(rows, ck.n_epochs, sub, cf, acc, mask);
-        else if (!ef && bin) epoch_loop<R, L, false, true>(rows, ck.n_epochs, sub, cf, acc, mask);
-        else if (ef && !bin) epoch_loop<R, L, true, false>(rows, ck.n_epochs, sub, cf, acc, mask);
-        else epoch_loop<R, L, true, true>(rows, ck.n_epochs, sub, cf, acc, mask);
-        if (ef) nvar += sub < ck.n_epochs ? (ck.n_epochs - sub + L - 1) / L : 0;
-
-        if (last) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                // log_p += -0.5*sum((res/errs)^2); log_p += -sum(log(errs))  (simulate.py:370-371)
-                double chi, logdet;
-                if (ef) {
-                    // chi^2 = 2^k T / Q;  -sum(log sigma) = -0.5 log(prod of variances), the table's
-                    // variances being stored times 2^k (two per epoch)
-                    renorm(acc[r]);                                   // Q into [1, 2): log() sees the same bits
-                    chi = group_sum<L>((acc[r].chi_ra / acc[r].prod) * S.chi_scale);
-                    const double part = log(acc[r].prod) + (double)(acc[r].esum - 2 * nvar * S.v_shift) * STN_LN2;
-                    logdet = -0.5 * group_sum<L>(part);
-                } else {
-                    chi = group_sum<L>(acc[r].chi_ra + acc[r].chi_dec);
-                    // host constant, counted once: by the split that holds the source's last chunk
-                    logdet = (ck.flags & kLast) ? S.neg_sum_log_err : 0.0;
-                }
-                if (P.out_chisq) {
-                    logl[r] += chi;
-                } else {
-                    logl[r] += -0.5 * chi;
-                    logl[r] += logdet;
-                }
-            }
-        }
+        src_chunk<R, L>(S, stage[it & 1], ck.n_epochs, sub, st);
+        if (last) src_fold<R, L>(P, S, (ck.flags & kLast) != 0, st, logl);
         __syncthreads();
     }
 
@@ -876,7 +911,7 @@ stn_stretch_propose_kernel(const double* __restrict__ x, const int64_t W, const 
     const int64_t j = (int64_t)(u01(r[2], r[3]) * (double)H);         // partner in the complementary half
     const double* xi = x + (half ? H + k : k) * ld;
     const double* xj = x + (half ? j : H + j) * ld;
-    for (int p = 0; p < P; ++p) y[k * P + p] = xj[p] + z * (xi[p] - xj[p]);
+    for (int p = 0; p < P; ++p) y[k * P + p] = fma(z, xi[p] - xj[p], xj[p]);
     z_out[k] = z;
 }
 
@@ -903,6 +938,192 @@ stn_stretch_accept_kernel(double* __restrict__ x, double* __restrict__ lp, const
     }
     const unsigned ballot = __ballot_sync(0xffffffffu, acc);
     if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(n_accept, (unsigned long long)__popc(ballot));
+}
+
+// ---------------------------------------------------------------------------------
+// Fused ensemble sampler: the WHOLE stretch-move loop in one persistent cooperative kernel.
+// Per half-step every thread proposes for its walkers, evaluates log prior + log L of the
+// proposal inline (the same per-source building blocks as K1, rows read straight from the
+// L1/L2-resident epoch tables: these are the small real-data problems, ~10 epochs per source,
+// where six launches per step cost more than the arithmetic) and accepts / rejects; the two
+// half-steps of a step are separated by one grid-wide barrier.  Same Philox counters and the
+// same arithmetic (plan lanes = 1, splits = 1) as the three-launch path, hence the same chain.
+// ---------------------------------------------------------------------------------
+#define STN_SAMPLER_MAX_P 64
+
+template <bool COH>
+__device__ double logpost_one(const ProbDev& P, const double* theta_row, int64_t ld) {
+    double logl[1] = {0.0};
+    const int64_t nidx[1] = {0};
+    SrcState<1> st;
+    st.mask = kChunk - 1;
+    st.nvar = 0;
+    for (int c = 0; c < P.n_chunks; ++c) {
+        const ChunkDev ck = P.chunks[c];
+        const SrcDev& S = P.src[ck.source];
+        if (ck.flags & kFirst) src_begin<1, COH>(P, S, theta_row, nidx, ld, STN_LAYOUT_AOS, st);
+        src_chunk<1, 1>(S, ck.rows, ck.n_epochs, 0, st);
+        if (ck.flags & kLast) src_fold<1, 1>(P, S, true, st, logl);
+    }
+    double v = logl[0];
+    if (P.n_a1dot > 0 || P.n_sini > 0) v += constraint_terms<COH>(P, theta_row, 0, ld, STN_LAYOUT_AOS);
+    if (P.n_prior > 0) {
+        const double lp = prior_terms<COH>(P, theta_row, 0, ld, STN_LAYOUT_AOS);
+        v = (lp == -CUDART_INF) ? lp : v + lp;
+    }
+    return v;
+}
+
+// Bytes of shared memory sampler_stage_problem needs (host and device agree through this one function).
+__host__ __device__ inline size_t sampler_align(size_t v) { return (v + 15) & ~(size_t)15; }
+
+__device__ __forceinline__ void block_copy(void* dst, const void* src, size_t bytes) {
+    // bytes is a multiple of 4 for every array copied here
+    uint32_t* d = static_cast<uint32_t*>(dst);
+    const uint32_t* q = static_cast<const uint32_t*>(src);
+    for (size_t i = threadIdx.x; i < bytes / 4; i += blockDim.x) d[i] = q[i];
+}
+
+// Copies everything ProbDev points to into shared memory (every CTA its own copy) and returns a ProbDev
+// whose pointers refer to the copies.  Layout: SrcDev[S] | ChunkDev[C] | fast tables | constraint and prior arrays.
+__device__ ProbDev sampler_stage_problem(const ProbDev& P, unsigned char* smem) {
+    ProbDev Q = P;
+    size_t off = 0;
+    SrcDev* src = reinterpret_cast<SrcDev*>(smem + off);
+    off += sampler_align(sizeof(SrcDev) * P.n_sources);
+    ChunkDev* chunks = reinterpret_cast<ChunkDev*>(smem + off);
+    off += sampler_align(sizeof(ChunkDev) * P.n_chunks);
+    block_copy(src, P.src, sizeof(SrcDev) * P.n_sources);
+    block_copy(chunks, P.chunks, sizeof(ChunkDev) * P.n_chunks);
+    __syncthreads();
+    // tables: one after the other in source order
+    size_t table_off = off;
+    for (int s = 0; s < P.n_sources; ++s) {
+        const size_t bytes = sizeof(double) * STN_FAST_ROW * (size_t)src[s].n_epochs;
+        block_copy(smem + table_off, P.src[s].fast_rows, bytes);
+        table_off += sampler_align(bytes);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        size_t o = off;
+        for (int s = 0; s < P.n_sources; ++s) {
+            const double* old_rows = src[s].fast_rows;
+            const double* new_rows = reinterpret_cast<const double*>(smem + o);
+            for (int c = 0; c < P.n_chunks; ++c)
+                if (chunks[c].source == s) chunks[c].rows = new_rows + (chunks[c].rows - old_rows);
+            src[s].fast_rows = new_rows;
+            o += sampler_align(sizeof(double) * STN_FAST_ROW * (size_t)src[s].n_epochs);
+        }
+    }
+    off = table_off;
+    auto take = [&](const void* g, size_t bytes) -> unsigned char* {
+        unsigned char* d = smem + off;
+        block_copy(d, g, bytes);
+        off += sampler_align(bytes);
+        return d;
+    };
+    Q.src = src;
+    Q.chunks = chunks;
+    Q.a1_src = reinterpret_cast<const int*>(take(P.a1_src, sizeof(int) * P.n_a1dot));
+    Q.a1_mu = reinterpret_cast<const double*>(take(P.a1_mu, sizeof(double) * P.n_a1dot));
+    Q.a1_sigma = reinterpret_cast<const double*>(take(P.a1_sigma, sizeof(double) * P.n_a1dot));
+    Q.sini_col = reinterpret_cast<const int*>(take(P.sini_col, sizeof(int) * P.n_sini));
+    Q.sini_mu = reinterpret_cast<const double*>(take(P.sini_mu, sizeof(double) * P.n_sini));
+    Q.sini_sigma = reinterpret_cast<const double*>(take(P.sini_sigma, sizeof(double) * P.n_sini));
+    Q.prior_kind = reinterpret_cast<const int*>(take(P.prior_kind, sizeof(int) * P.n_prior));
+    Q.prior_a = reinterpret_cast<const double*>(take(P.prior_a, sizeof(double) * P.n_prior));
+    Q.prior_b = reinterpret_cast<const double*>(take(P.prior_b, sizeof(double) * P.n_prior));
+    Q.sinlim_col = reinterpret_cast<const int*>(take(P.sinlim_col, sizeof(int) * P.n_sinlim));
+    Q.sinlim_lo = reinterpret_cast<const double*>(take(P.sinlim_lo, sizeof(double) * P.n_sinlim));
+    Q.sinlim_hi = reinterpret_cast<const double*>(take(P.sinlim_hi, sizeof(double) * P.n_sinlim));
+    __syncthreads();
+    return Q;
+}
+
+constexpr int kSamplerThreads = 256;
+
+// All CTAs of the launch meet here.  cluster_mode: the launch is ONE thread-block cluster (up to 16 CTAs
+// = 4096 proposals per half-step) and this is the hardware cluster barrier (release / acquire: the walkers
+// just written by other CTAs are visible afterwards); otherwise a cooperative launch and the grid barrier.
+__device__ __forceinline__ void sampler_barrier(bool cluster_mode) {
+    namespace cg = cooperative_groups;
+    if (cluster_mode) {
+        asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+    } else {
+        cg::this_grid().sync();
+    }
+}
+
+__global__ void __launch_bounds__(kSamplerThreads)
+stn_ensemble_kernel(const ProbDev P0, double* x, double* lp, const int64_t W, const int64_t ld, const double a,
+                    const uint64_t seed, const uint64_t step0, const int64_t n_steps, const int64_t thin,
+                    double* chain, double* lnprob, unsigned long long* n_accept, const int cluster_mode) {
+    // The whole problem description -- sources, chunk list, epoch tables, constraints, prior -- is copied
+    // to shared memory once: the barrier between half-steps invalidates L1 (acquire), so anything left in
+    // global memory would be re-fetched from L2 (~700 cycles per dependent load) in every half-step.
+    extern __shared__ __align__(16) unsigned char sampler_smem[];
+    const ProbDev Q = sampler_stage_problem(P0, sampler_smem);
+    const ProbDev& P = Q;
+    const int np = P.n_params;
+    const int64_t H = W / 2;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t Hpad = (H + 31) / 32 * 32;             // whole warps walk the loop together
+    unsigned long long accepted = 0;
+    double y[STN_SAMPLER_MAX_P];
+    for (int64_t t = 0; t < n_steps; ++t) {
+        const uint64_t step = step0 + (uint64_t)t;
+        for (int half = 0; half < 2; ++half) {
+            for (int64_t kk = gtid; kk < Hpad; kk += nthreads) {
+                const bool valid = kk < H;
+                const int64_t k = valid ? kk : H - 1;
+                // this walker's row and log-posterior do not depend on the random numbers: their L2 round trip
+                // (the barrier invalidated L1) overlaps the Philox rounds
+                const int64_t i = half ? H + k : k;
+                const double* xi = x + i * ld;
+                for (int p = 0; p < np; ++p) y[p] = __ldcg(xi + p);
+                const double lp_i = __ldcg(lp + i);
+                uint32_t r[4];
+                philox4x32_10((uint32_t)k, (uint32_t)(k >> 32), (uint32_t)step,
+                              (uint32_t)(step >> 32) ^ (half ? 0x80000000u : 0u), (uint32_t)seed, (uint32_t)(seed >> 32), r);
+                const double u = u01(r[0], r[1]);
+                const double tt = (a - 1.0) * u + 1.0;
+                const double z = tt * tt / a;
+                const int64_t j = (int64_t)(u01(r[2], r[3]) * (double)H);
+                const double* xj = x + (half ? j : H + j) * ld;
+                uint32_t r2[4];
+                philox4x32_10((uint32_t)k, (uint32_t)(k >> 32), (uint32_t)step,
+                              (uint32_t)(step >> 32) ^ (half ? 0xC0000000u : 0x40000000u), (uint32_t)seed,
+                              (uint32_t)(seed >> 32), r2);                        // accept draw, while the partner row arrives
+                for (int p = 0; p < np; ++p) {
+                    const double vj = __ldcg(xj + p);
+                    y[p] = fma(z, y[p] - vj, vj);
+                }
+                const double lpy = logpost_one<true>(P, y, np);
+                const double lnq = (double)(np - 1) * log(z) + lpy - lp_i;
+                const bool acc = valid && (lpy > -CUDART_INF) && (lpy == lpy) && (log(u01(r2[0], r2[1])) < lnq);
+                if (acc) {
+                    for (int p = 0; p < np; ++p) x[i * ld + p] = y[p];
+                    lp[i] = lpy;
+                    ++accepted;
+                }
+            }
+            sampler_barrier(cluster_mode != 0);        // the other half reads these walkers next
+        }
+        if (chain != nullptr && (t + 1) % thin == 0) {
+            const int64_t slot = (t + 1) / thin - 1;
+            for (int64_t e = gtid; e < W * np; e += nthreads) {
+                const int64_t w = e / np;
+                chain[slot * W * np + e] = __ldcg(x + w * ld + (e - w * np));
+            }
+            if (lnprob != nullptr)
+                for (int64_t w = gtid; w < W; w += nthreads) lnprob[slot * W + w] = __ldcg(lp + w);
+            sampler_barrier(cluster_mode != 0);        // half-step 0 of the next step overwrites rows that are being copied
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) accepted += __shfl_xor_sync(0xffffffffu, accepted, o);
+    if ((threadIdx.x & 31) == 0 && accepted) atomicAdd(n_accept, accepted);
 }
 
 // ---------------------------------------------------------------------------------
@@ -962,6 +1183,8 @@ struct StnCtx {
     cudaStream_t timing_stream = nullptr;
     double* gather_buf = nullptr;       // stn_multi_loglike_dev: this device's slice before the peer copy
     int64_t gather_elems = 0;
+    double* sampler_buf = nullptr;      // stn_ensemble_run (three-launch engine): proposals, stretch factors, log-posteriors
+    int64_t sampler_elems = 0;
 };
 
 // Several contexts of the same problem, one per device, driven as one (stn_multi_*).
@@ -1552,6 +1775,7 @@ int stn_destroy(StnCtx* ctx) {
         if (ctx->streams[i]) cudaStreamDestroy(ctx->streams[i]);
     }
     if (ctx->gather_buf) cudaFree(ctx->gather_buf);
+    if (ctx->sampler_buf) cudaFree(ctx->sampler_buf);
     if (ctx->timing_stream) cudaStreamDestroy(ctx->timing_stream);
     delete ctx;
     return STN_OK;
@@ -1978,6 +2202,132 @@ int stn_stretch_accept(int device, double* x_dev, double* lp_dev, int64_t n_walk
         x_dev, lp_dev, n_walkers, n_params, ld, half, seed, step, y_dev, z_dev, lpy_dev,
         reinterpret_cast<unsigned long long*>(n_accept_dev));
     STN_CUDA(cudaGetLastError());
+    return STN_OK;
+}
+
+int stn_ensemble_run(StnCtx* ctx, double* x_dev, double* lp_dev, int64_t n_walkers, int64_t ld, double a,
+                     uint64_t seed, uint64_t step0, int64_t n_steps, int64_t thin, double* chain_dev,
+                     double* lnprob_dev, int64_t* n_accept_dev, int mode, int plan, int engine, void* stream) {
+    if (!ctx || !x_dev || !lp_dev || !n_accept_dev) return fail(STN_ERR_INVALID, "null argument");
+    if (!ctx->has_prior) return fail(STN_ERR_INVALID, "stn_ensemble_run needs stn_set_prior first");
+    const int P = ctx->prob.n_params;
+    if (n_walkers < 2 || (n_walkers & 1) || ld < P || !(a > 1.0) || n_steps < 0 || thin < 1)
+        return fail(STN_ERR_INVALID, "stretch move needs an even number of walkers >= 2, ld >= P, a > 1, thin >= 1");
+    if (mode != STN_MODE_FAST && mode != STN_MODE_STRICT) return fail(STN_ERR_INVALID, "bad mode %d", mode);
+    if (n_steps == 0) return STN_OK;
+    STN_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t H = n_walkers / 2;
+    // engine 0: choose; 1: persistent cooperative kernel; 2: three launches per half-step
+    int64_t evals = 0;
+    for (int e : ctx->n_epochs) evals += e;
+    const bool can_fuse = mode == STN_MODE_FAST && P <= STN_SAMPLER_MAX_P && (plan == 0 || plan == make_plan(1, 1));
+    if (engine == 1 && !can_fuse)
+        return fail(STN_ERR_INVALID, "the persistent sampler kernel needs mode fast, plan 0 or lanes=1|splits=1, P <= %d",
+                    STN_SAMPLER_MAX_P);
+    bool fuse = engine == 1 || (engine == 0 && can_fuse && evals <= 512);
+    int grid = 0;
+    size_t smem = 0;
+    if (fuse) {
+        // shared-memory image of the problem (sampler_stage_problem's layout)
+        const ProbDev& pp = ctx->prior_prob;
+        smem = sampler_align(sizeof(SrcDev) * pp.n_sources) + sampler_align(sizeof(ChunkDev) * pp.n_chunks);
+        for (int e : ctx->n_epochs) smem += sampler_align(sizeof(double) * STN_FAST_ROW * (size_t)e);
+        smem += 3 * sampler_align(8 * (size_t)pp.n_a1dot) + 3 * sampler_align(8 * (size_t)pp.n_sini) +
+                3 * sampler_align(8 * (size_t)pp.n_prior) + 3 * sampler_align(8 * (size_t)pp.n_sinlim);
+        if (smem > 200 * 1024) {
+            if (engine == 1) return fail(STN_ERR_INVALID, "the problem (%zu bytes) does not fit the persistent kernel's shared memory", smem);
+            fuse = false;
+        }
+    }
+    if (fuse) {
+        int per_sm = 0;
+        STN_CUDA(cudaFuncSetAttribute(stn_ensemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        STN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stn_ensemble_kernel, kSamplerThreads, smem));
+        const int64_t want = (H + kSamplerThreads - 1) / kSamplerThreads;
+        const int64_t cap = (int64_t)per_sm * ctx->sm_count;
+        if (cap < 1) {
+            if (engine == 1) return fail(STN_ERR_CUDA, "the persistent sampler kernel does not fit on this device");
+            fuse = false;
+        }
+        grid = (int)(want < cap ? want : cap);
+    }
+    if (fuse) {
+        ProbDev prob = ctx->prior_prob;
+        prob.out_chisq = 0;
+        prob.n_extra_out = 0;
+        unsigned long long* nacc = reinterpret_cast<unsigned long long*>(n_accept_dev);
+        (void)cudaGetLastError();
+        // up to 16 CTAs: one thread-block cluster, hardware barrier between half-steps
+        if (grid <= 16 && STN_SAMPLER_CLUSTER) {
+            bool ok = true;
+            if (grid > 8)
+                ok = cudaFuncSetAttribute(stn_ensemble_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+            if (ok) {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned)grid);
+                cfg.blockDim = dim3(kSamplerThreads);
+                cfg.dynamicSmemBytes = smem;
+                cfg.stream = st;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = (unsigned)grid;
+                at[0].val.clusterDim.y = 1;
+                at[0].val.clusterDim.z = 1;
+                cfg.attrs = at;
+                cfg.numAttrs = 1;
+                const cudaError_t e = cudaLaunchKernelEx(&cfg, stn_ensemble_kernel, prob, x_dev, lp_dev, n_walkers, ld, a, seed,
+                                                         step0, n_steps, thin, chain_dev, lnprob_dev, nacc, 1);
+                if (e == cudaSuccess) {
+                    ctx->launches++;
+                    return STN_OK;
+                }
+            }
+            (void)cudaGetLastError();                     // cluster launch refused: fall back to the cooperative grid
+        }
+        int cluster_mode = 0;
+        void* args[] = {&prob, &x_dev, &lp_dev, &n_walkers, &ld, &a, &seed, &step0, &n_steps, &thin, &chain_dev,
+                        &lnprob_dev, &nacc, &cluster_mode};
+        STN_CUDA(cudaLaunchCooperativeKernel((const void*)stn_ensemble_kernel, dim3((unsigned)grid), dim3(kSamplerThreads), args, smem, st));
+        ctx->launches++;
+        return STN_OK;
+    }
+    // generic path (long series: the throughput kernel per half-step), launches issued from here
+    // instead of from Python; proposals and their log-posteriors live in the context's scratch
+    if (plan == 0) plan = pick_plan(ctx, H);
+    const int64_t need = H * P + 2 * H;
+    if (ctx->sampler_elems < need) {
+        STN_CUDA(cudaStreamSynchronize(st));
+        if (ctx->sampler_buf) cudaFree(ctx->sampler_buf);
+        ctx->sampler_buf = nullptr;
+        ctx->sampler_elems = 0;
+        STN_CUDA(cudaMalloc(&ctx->sampler_buf, (size_t)need * sizeof(double)));
+        ctx->sampler_elems = need;
+    }
+    double* y = ctx->sampler_buf;
+    double* z = y + H * P;
+    double* lpy = z + H;
+    for (int64_t t = 0; t < n_steps; ++t) {
+        for (int half = 0; half < 2; ++half) {
+            int rc = stn_stretch_propose(ctx->device, x_dev, n_walkers, P, ld, half, a, seed, step0 + (uint64_t)t, y, z, stream);
+            if (rc) return rc;
+            rc = launch_loglike(ctx, y, H, P, STN_LAYOUT_AOS, mode, plan, lpy, st, 1);
+            if (rc) return rc;
+            rc = stn_stretch_accept(ctx->device, x_dev, lp_dev, n_walkers, P, ld, half, seed, step0 + (uint64_t)t, y, z, lpy,
+                                    n_accept_dev, stream);
+            if (rc) return rc;
+            ctx->launches += 2;
+        }
+        if (chain_dev && (t + 1) % thin == 0) {
+            const int64_t slot = (t + 1) / thin - 1;
+            STN_CUDA(cudaMemcpy2DAsync(chain_dev + slot * n_walkers * P, (size_t)P * sizeof(double), x_dev,
+                                       (size_t)ld * sizeof(double), (size_t)P * sizeof(double), (size_t)n_walkers,
+                                       cudaMemcpyDeviceToDevice, st));
+            if (lnprob_dev)
+                STN_CUDA(cudaMemcpyAsync(lnprob_dev + slot * n_walkers, lp_dev, (size_t)n_walkers * sizeof(double),
+                                         cudaMemcpyDeviceToDevice, st));
+        }
+    }
     return STN_OK;
 }
 

@@ -262,18 +262,23 @@ class EnsembleSampler(object):
 
 
 class FusedEnsembleSampler(object):
-    """The same stretch move with every ensemble half-step as THREE library launches
-    (stn_stretch_propose -> stn_logpost -> stn_stretch_accept): walkers, proposals and
-    log-probabilities never leave the GPU and no torch arithmetic runs in the loop.
+    """The same stretch move entirely inside the library (stn_ensemble_run): walkers, proposals and
+    log-probabilities never leave the GPU, no torch arithmetic and no Python runs in the loop.
 
         s = FusedEnsembleSampler(likelihood, prior, nwalkers, seed=1)
         s.run(p0, nsteps, thin=10);  s.chain  # (nsteps // thin, nwalkers, ndim) CUDA tensor
 
-    Random numbers are counter-based (Philox keyed by `seed`): a run is reproducible and does
-    not depend on launch geometry.  Columns of p0 / chain follow prior.keys.
+    engine='auto' picks per problem: short series (the reference's real-data regime, ~10 epochs per
+    source) run as ONE persistent cooperative kernel -- propose, log prior + log L inline, accept, a
+    grid-wide barrier between the two half-steps, `nsteps` steps per launch; long series use the
+    throughput kernel, three launches per half-step issued from C.  'persistent' / 'launches' force one.
+    Random numbers are counter-based (Philox keyed by `seed`): a run is reproducible, independent of
+    launch geometry and of the engine.  Columns of p0 / chain follow prior.keys.
     """
 
-    def __init__(self, likelihood, prior, nwalkers, a=2.0, seed=0, mode=None, plan=None):
+    ENGINES = {'auto': 0, 'persistent': 1, 'launches': 2}
+
+    def __init__(self, likelihood, prior, nwalkers, a=2.0, seed=0, mode=None, plan=None, engine='auto'):
         import torch
         from . import _lib
         ndim = prior.ndim
@@ -289,8 +294,10 @@ class FusedEnsembleSampler(object):
         if self.ctx.prior is not prior:
             self.ctx.set_prior(prior)
         self.mode = likelihood.mode if mode is None else _lib.MODES[mode]
-        # the plan is fixed from the half-ensemble size once, so every step sums in the same order
-        self.plan = self.ctx.auto_plan(nwalkers // 2) if plan is None else int(plan)
+        # lanes = 1, splits = 1 is the summation order of the persistent kernel; the launch engine uses the
+        # same plan unless told otherwise, so both engines give the same chain
+        self.plan = _lib.make_plan(1, 1) if plan is None else int(plan)
+        self.engine = self.ENGINES[engine]
         self.step = 0
         self.chain = None
         self.lnprob = None
@@ -299,38 +306,29 @@ class FusedEnsembleSampler(object):
 
     def run(self, p0, nsteps, thin=1, store=True):
         torch = self.torch
-        W, P, H = self.nwalkers, self.ndim, self.nwalkers // 2
+        from . import _lib
+        W, P = self.nwalkers, self.ndim
         dev = self.device
         x = torch.as_tensor(np.asarray(p0) if not _is_torch(p0) else p0).to(dev, torch.float64).contiguous().clone()
         if tuple(x.shape) != (W, P):
             raise ValueError('p0 must be (nwalkers, ndim)')
         lp = torch.empty(W, dtype=torch.float64, device=dev)
-        y = torch.empty((H, P), dtype=torch.float64, device=dev)
-        z = torch.empty(H, dtype=torch.float64, device=dev)
-        lpy = torch.empty(H, dtype=torch.float64, device=dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        from . import _lib
-        self.ctx.logpost_ptr(x.data_ptr(), W, P, _lib.LAYOUT_AOS, self.mode, self.ctx.auto_plan(W), lp.data_ptr(), stream)
+        self.ctx.logpost_ptr(x.data_ptr(), W, P, _lib.LAYOUT_AOS, self.mode, self.plan, lp.data_ptr(), stream)
         if not bool(torch.isfinite(lp).all()):
             raise ValueError('initial walkers must have finite log-probability')
         nkeep = nsteps // thin if store else 0
+        chain_ptr = lnprob_ptr = None
         if store:
             self.chain = torch.empty((nkeep, W, P), dtype=torch.float64, device=dev)
             self.lnprob = torch.empty((nkeep, W), dtype=torch.float64, device=dev)
-        d = self.like.device
-        for t in range(nsteps):
-            for half in (0, 1):
-                self.check(self.lib.stn_stretch_propose(d, x.data_ptr(), W, P, P, half, self.a, self.seed, self.step,
-                                                        y.data_ptr(), z.data_ptr(), stream))
-                self.ctx.logpost_ptr(y.data_ptr(), H, P, _lib.LAYOUT_AOS, self.mode, self.plan, lpy.data_ptr(), stream)
-                self.check(self.lib.stn_stretch_accept(d, x.data_ptr(), lp.data_ptr(), W, P, P, half, self.seed,
-                                                       self.step, y.data_ptr(), z.data_ptr(), lpy.data_ptr(),
-                                                       self._nacc.data_ptr(), stream))
-            self.step += 1
-            self.nproposed += W
-            if store and (t + 1) % thin == 0 and (t + 1) // thin <= nkeep:
-                self.chain[(t + 1) // thin - 1].copy_(x)
-                self.lnprob[(t + 1) // thin - 1].copy_(lp)
+            if nkeep:
+                chain_ptr, lnprob_ptr = self.chain.data_ptr(), self.lnprob.data_ptr()
+        self.check(self.lib.stn_ensemble_run(self.ctx.handle, x.data_ptr(), lp.data_ptr(), W, P, self.a, self.seed,
+                                             self.step, nsteps, thin, chain_ptr, lnprob_ptr, self._nacc.data_ptr(),
+                                             self.mode, self.plan, self.engine, stream))
+        self.step += nsteps
+        self.nproposed += W * nsteps
         self.last = (x, lp)
         return x, lp
 

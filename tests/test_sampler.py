@@ -163,8 +163,8 @@ def test_fused_log_posterior_equals_prior_plus_likelihood():
 
 @pytest.mark.gpu
 def test_fused_sampler_matches_torch_sampler_statistically():
-    """Three launches per half-step (propose / stn_logpost / accept): same posterior as the
-    torch-op sampler and the truth inside it; reproducible for a given seed."""
+    """stn_ensemble_run: same posterior as the torch-op sampler and the truth inside it; reproducible
+    for a given seed; the persistent-kernel engine and the three-launches engine give the SAME chain."""
     from sterne_b200.sampler import FusedEnsembleSampler
     case = synthetic.config2()
     like = case.likelihood()
@@ -186,14 +186,40 @@ def test_fused_sampler_matches_torch_sampler_statistically():
     assert (np.abs(flat_f.std(0) / sd - 1.0)).max() < 0.1
     astrometric = [i for i, k in enumerate(case.names) if not k.startswith('efac')]
     assert (np.abs(flat_f.mean(0) - case.truth_vector()) / flat_f.std(0))[astrometric].max() < 4.0
-    # log-probabilities carried by the sampler are the posterior's
+    # log-probabilities carried by the sampler are the posterior's, bit for bit (plan lanes = 1, splits = 1)
+    from sterne_b200._lib import make_plan
     x, lp = f.last
-    assert torch.equal(like.log_posterior_batch(x, prior, plan=like._context(prior.keys).auto_plan(nw)), lp) or \
-        ((like.log_posterior_batch(x, prior) - lp).abs().max().item() < 1e-6)
-    # reproducible
-    g = FusedEnsembleSampler(like, prior, nw, seed=11)
-    g.run(p0, 50, store=False)
-    h = FusedEnsembleSampler(like, prior, nw, seed=11)
-    h.run(p0, 50, store=False)
-    assert torch.equal(g.last[0], h.last[0])
+    assert torch.equal(like.log_posterior_batch(x, prior, plan=make_plan(1, 1)), lp)
+    # reproducible, and independent of the engine: one persistent cooperative kernel == three launches per half-step
+    g = FusedEnsembleSampler(like, prior, nw, seed=11, engine='persistent')
+    g.run(p0, 50, thin=5)
+    h = FusedEnsembleSampler(like, prior, nw, seed=11, engine='launches')
+    h.run(p0, 50, thin=5)
+    assert torch.equal(g.last[0], h.last[0]) and torch.equal(g.last[1], h.last[1])
+    assert torch.equal(g.chain, h.chain) and torch.equal(g.lnprob, h.lnprob)
+    assert g.acceptance_fraction == h.acceptance_fraction
+    # continuing a run == one longer run (the step counter carries the random stream)
+    k = FusedEnsembleSampler(like, prior, nw, seed=11)
+    k.run(p0, 20, store=False)
+    k.run(k.last[0], 30, store=False)
+    assert torch.equal(k.last[0], g.last[0])
+    # odd walker counts per warp / block and a binary problem with priors of every kind
+    case3 = synthetic.config3('dots')
+    like3 = case3.likelihood()
+    lim3 = {}
+    for kname in case3.names:
+        lo, hi = case3.box[kname]
+        lim3[kname] = [0.1, 3.0, 'Sine'] if kname.startswith('incl') else \
+            [case3.truth[kname], 1.5, 'Gaussian'] if kname.startswith('mu_a') else [lo, hi, 'Uniform']
+    prior3 = BoxPrior(lim3, {'sin_incl_limits_constraints': {'incl_0': [0.3, 0.999]}})
+    nw3 = 166
+    half3 = np.array([0.5 * (case3.box[kname][1] - case3.box[kname][0]) for kname in case3.names])
+    p3 = case3.truth_vector() + 0.02 * half3 * np.random.default_rng(5).standard_normal((nw3, case3.n_params))
+    a3 = FusedEnsembleSampler(like3, prior3, nw3, seed=3, engine='persistent')
+    a3.run(p3, 40, thin=1)
+    b3 = FusedEnsembleSampler(like3, prior3, nw3, seed=3, engine='launches')
+    b3.run(p3, 40, thin=1)
+    assert torch.equal(a3.chain, b3.chain) and torch.equal(a3.lnprob, b3.lnprob)
+    assert 0.02 < a3.acceptance_fraction < 0.98
+    like3.close()
     like.close()

@@ -50,13 +50,14 @@ for name, mk in (('config1', synthetic.config1), ('config2', synthetic.config2),
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
     r['sampler_4096_walkers_steps_per_s'] = 200 / dt
     r['sampler_loglike_evals_per_s'] = 200 * 4096 * case.evals_per_sample / dt
-    f = FusedEnsembleSampler(like, prior, 4096, seed=1)
-    f.run(p0, 50, store=False)
-    torch.cuda.synchronize(); t0 = time.perf_counter()
-    f.run(f.last[0], 2000, store=False)
-    torch.cuda.synchronize(); dt = time.perf_counter() - t0
-    r['fused_sampler_4096_walkers_steps_per_s'] = 2000 / dt
-    r['fused_sampler_loglike_evals_per_s'] = 2000 * 4096 * case.evals_per_sample / dt
+    for engine in ('persistent', 'launches'):
+        f = FusedEnsembleSampler(like, prior, 4096, seed=1, engine=engine)
+        f.run(p0, 50, store=False)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        f.run(f.last[0], 4000, store=False)
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        r['fused_sampler_%s_4096_walkers_steps_per_s' % engine] = 4000 / dt
+        r['fused_sampler_%s_loglike_evals_per_s' % engine] = 4000 * 4096 * case.evals_per_sample / dt
     res[name] = r
     like.close()
 print(json.dumps(res))
