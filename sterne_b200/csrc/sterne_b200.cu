@@ -36,6 +36,7 @@
 #define STN_ASSERT(x) ((void)0)
 #endif
 #include <cstdio>
+#include <cstdlib>
 #include <cstdarg>
 #include <cstring>
 #include <cmath>
@@ -590,8 +591,13 @@ __device__ __forceinline__ void store_result(const ProbDev& P, double* __restric
 __host__ __device__ constexpr int threads_for(int R) { return R > 2 ? STN_THREADS_R3 : (R == 2 ? STN_THREADS_R2 : kThreads); }
 __host__ __device__ constexpr int minblocks_for(int R) { return R > 2 ? STN_MINBLOCKS_R3 : (R == 2 ? STN_MINBLOCKS_R2 : 2); }
 
-template <int R, int L>
-__global__ void __launch_bounds__(threads_for(R), minblocks_for(R))
+// TPB: threads per CTA (default: the shape chosen for R); TPB = kTailThreads is the small-CTA form of the
+// R = 1 kernel that finishes the last, partly filled wave of a big launch
+constexpr int kTailThreads = 64;
+__host__ __device__ constexpr int minblocks_tpb(int R, int tpb) { return tpb == threads_for(R) ? minblocks_for(R) : 8; }
+
+template <int R, int L, int TPB = threads_for(R)>
+__global__ void __launch_bounds__(TPB, minblocks_tpb(R, TPB))
 stn_loglike_fast_kernel(const ProbDev P, const double* __restrict__ theta, const int64_t N,
                         const int64_t ld, const int layout, double* __restrict__ out,
                         double* __restrict__ partial) {
@@ -601,7 +607,7 @@ stn_loglike_fast_kernel(const ProbDev P, const double* __restrict__ theta, const
     const int tid = threadIdx.x;
     const int sub = tid % L;
     const int grp = tid / L;
-    constexpr int G = threads_for(R) / L;               // sample groups per CTA
+    constexpr int G = TPB / L;                          // sample groups per CTA
     const int64_t tile_base = (int64_t)blockIdx.x * (G * R);
 
     int64_t nidx[R];
@@ -1290,15 +1296,15 @@ int pick_plan(const StnCtx* ctx, int64_t n) {
     return make_plan(L, K);
 }
 
-template <int R, int L>
+template <int R, int L, int TPB = threads_for(R)>
 int launch_fast(StnCtx* ctx, const ProbDev& prob, const double* theta, int64_t n, int64_t ld, int layout,
                 double* out, cudaStream_t st, int splits, double* partial) {
-    constexpr int per_cta = (threads_for(R) / L) * R;
+    constexpr int per_cta = (TPB / L) * R;
     const int64_t grid = (n + per_cta - 1) / per_cta;
     if (grid > 0x7fffffffLL) return fail(STN_ERR_INVALID, "batch too large for one launch");
     dim3 g((unsigned)grid, (unsigned)splits, 1);
     (void)cudaGetLastError();      // other CUDA users of this process (torch) may have left a stale error
-    stn_loglike_fast_kernel<R, L><<<g, threads_for(R), 0, st>>>(prob, theta, n, ld, layout, out, partial);
+    stn_loglike_fast_kernel<R, L, TPB><<<g, TPB, 0, st>>>(prob, theta, n, ld, layout, out, partial);
     STN_CUDA(cudaGetLastError());
     ctx->launches++;
     if (splits > 1) {
@@ -1366,16 +1372,20 @@ int launch_loglike(StnCtx* ctx, const double* theta, int64_t n, int64_t ld, int 
             if (R > 1) {
                 // Wave quantisation: every CTA of the big kernel runs for the same time, so a last wave
                 // that is only partly full costs a whole wave (4.6 waves at 2^19 vectors = 8 % lost).  The
-                // samples beyond the last FULL wave go to the R = 1 kernel instead: its CTAs hold a third
-                // (half) of the samples, so that tail finishes in well under one big-kernel wave.  R never
-                // changes a result bit, so this is invisible in the output.
+                // samples beyond the last FULL wave go to the R = 1 kernel in 64-thread CTAs instead: a third
+                // (half) of the samples per thread and many small CTAs that spread evenly over the SMs, so
+                // that tail finishes in well under one big-kernel wave.  R never changes a result bit, so
+                // this is invisible in the output.
                 const int bigR = ctx->efac_heavy ? STN_RBIG_EFAC : STN_RBIG;
                 const int64_t tile = (int64_t)threads_for(bigR) * bigR;
                 const int64_t slots = (int64_t)ctx->sm_count * minblocks_for(bigR);
                 const int64_t tiles = (n + tile - 1) / tile;
                 const int64_t n_main = (tiles / slots) * slots * tile;
-                const int64_t cap1 = (int64_t)ctx->sm_count * minblocks_for(1) * threads_for(1);
-                if (splits == 1 && n_main > 0 && n_main < n && n - n_main <= cap1 && STN_TAIL_SMALL_R) {
+                const int64_t cap1 = (int64_t)ctx->sm_count * minblocks_tpb(1, kTailThreads) * kTailThreads;
+                // measured (profiles/r02_tail_*.json): worth it only when the leftover would fill more than about
+                // half a wave -- 6.39 -> 6.22 ms at 2^19 vectors (0.61 of a wave left) but 23.4 -> 23.7 ms at 2^21 (0.45)
+                const bool worth = 20 * (tiles - (tiles / slots) * slots) >= 11 * slots;
+                if (splits == 1 && n_main > 0 && n_main < n && n - n_main <= cap1 && worth && STN_TAIL_SMALL_R) {
                     int rc = ctx->efac_heavy
                                  ? launch_fast<STN_RBIG_EFAC, 1>(ctx, prob, theta, n_main, ld, layout, out, st, 1, nullptr)
                                  : launch_fast<STN_RBIG, 1>(ctx, prob, theta, n_main, ld, layout, out, st, 1, nullptr);
@@ -1383,7 +1393,7 @@ int launch_loglike(StnCtx* ctx, const double* theta, int64_t n, int64_t ld, int 
                     ProbDev tail = prob;
                     for (int k = 0; k < tail.n_extra_out; ++k) tail.extra_out[k] += n_main;
                     const double* th_tail = layout == STN_LAYOUT_AOS ? theta + n_main * ld : theta + n_main;
-                    return launch_fast<1, 1>(ctx, tail, th_tail, n - n_main, ld, layout, out + n_main, st, 1, nullptr);
+                    return launch_fast<1, 1, kTailThreads>(ctx, tail, th_tail, n - n_main, ld, layout, out + n_main, st, 1, nullptr);
                 }
                 if (ctx->efac_heavy) STN_GO(STN_RBIG_EFAC, 1);
                 STN_GO(STN_RBIG, 1);
@@ -1440,7 +1450,7 @@ void host_pipe_drain(StnCtx* ctx) {
 }
 
 // Rows of the k-th chunk: a short first chunk (its H2D copy is the only one nothing overlaps),
-// doubling up to 2^20 rows (every chunk boundary costs a partly filled wave of CTAs).
+// growing fourfold up to 2^20 rows (every chunk boundary costs a partly filled wave of CTAs).
 #ifndef STN_HOST_CHUNK_LOG2
 #define STN_HOST_CHUNK_LOG2 20
 #endif
@@ -1466,11 +1476,34 @@ void big_memcpy(void* dst, const void* src, size_t bytes) {
     std::memcpy(dst, src, part < bytes ? part : bytes);
     for (std::thread& th : pool) th.join();
 }
+// Tuning overrides (environment, read once): STN_HOST_FIRST_LOG2 = log2 of the first chunk's rows,
+// STN_HOST_GROWTH = factor between consecutive chunks.
+struct HostSchedule {
+    int64_t first = 0;
+    int growth = 0;
+    HostSchedule() {
+        if (const char* e = std::getenv("STN_HOST_FIRST_LOG2")) first = (int64_t)1 << std::atoi(e);
+        if (const char* e = std::getenv("STN_HOST_GROWTH")) growth = std::atoi(e);
+    }
+};
+const HostSchedule& host_schedule() {
+    static const HostSchedule s;
+    return s;
+}
+
 int64_t first_chunk_rows(int64_t n) {
+    const HostSchedule& hs = host_schedule();
+    if (hs.first > 0) return hs.first < n ? hs.first : n;
     int64_t r = n / 32;
     if (r > ((int64_t)1 << 15)) r = (int64_t)1 << 15;
     if (r < 4096) r = 4096;
     return r < n ? r : n;
+}
+
+int64_t next_chunk_rows(int64_t rows) {
+    const int g = host_schedule().growth > 1 ? host_schedule().growth : 4;    // measured: 4 beats 2 and 8 (profiles/r02_host_schedule.txt)
+    if (rows >= kChunkRowsMax) return kChunkRowsMax;
+    return rows * g < kChunkRowsMax ? rows * g : kChunkRowsMax;
 }
 
 // One slice of a host batch on this context's device: H2D, kernel(s), D2H, synchronised on return.
@@ -1589,7 +1622,7 @@ int run_host(StnCtx* ctx, const double* theta_host, int64_t n, int64_t ld, int l
                 pend[slot].lo = lo; pend[slot].m = m; pend[slot].live = true;
             }
             lo += m;
-            if (rows < kChunkRowsMax) rows = rows * 2 < kChunkRowsMax ? rows * 2 : kChunkRowsMax;
+            rows = next_chunk_rows(rows);
         }
         // the chunks still in flight, oldest first
         for (int j = 0; j < StnCtx::kSlots; ++j) {

@@ -9,6 +9,7 @@ ap.add_argument('--steps', type=int, default=5)
 ap.add_argument('--log2n', type=int, default=22)
 ap.add_argument('--out', default=os.path.join(ROOT, 'gpurun_out', 'kvariants.json'))
 ap.add_argument('--only', default='')
+ap.add_argument('--plan', type=int, default=0)
 a = ap.parse_args()
 libs = sorted(glob.glob(os.path.join(ROOT, 'build_variants', 'lib_*.so')))
 if a.only:
@@ -17,7 +18,7 @@ res = []
 for lib in libs:
     env = dict(os.environ, STERNE_B200_LIB=lib)
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'kbench.py'), '--variants', a.variants, '--steps',
-                        str(a.steps), '--log2n', str(a.log2n), '--check'], env=env, capture_output=True, text=True)
+                        str(a.steps), '--log2n', str(a.log2n), '--plan', str(a.plan), '--check'], env=env, capture_output=True, text=True)
     line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ''
     try:
         d = json.loads(line)
