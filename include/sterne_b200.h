@@ -247,6 +247,22 @@ int stn_multi_loglike_dev(StnMulti* m, const double* const* theta_dev, const int
                           int64_t ld, int layout, int mode, int plan, double* out_dev,
                           int out_device);
 
+/* One walker ensemble advanced by ALL devices of the multi-context (what the reference does in one
+ * emcee process, simulate.py:191-192, for ensembles too large for one GPU).  Every device holds a full
+ * copy of the walkers, x_dev[g] (W, ld >= P) and lp_dev[g] (W), identical on entry (lp = current
+ * log-posteriors).  In each half-step device g proposes and evaluates the proposals of its slice of the
+ * half, and its accept kernel stores the accepted walkers into EVERY device's copy through peer-mapped
+ * pointers -- the exchange of the updated half over NVLink is fused into the kernel; the devices are
+ * ordered by events, not by the host.  Random numbers are keyed by global walker indices and the plan
+ * defaults to lanes = 1 | splits = 1, so the chain is bit-identical to stn_ensemble_run's on one device.
+ * chain_dev / lnprob_dev (nullable) live on the first device; *n_accept_host is incremented.  Needs
+ * stn_multi_set_prior and peer access between all devices (STN_ERR_DEVICE otherwise).  Synchronous. */
+int stn_multi_set_prior(StnMulti* m, const StnPrior* prior);
+int stn_multi_ensemble_run(StnMulti* m, double* const* x_dev, double* const* lp_dev, int64_t n_walkers,
+                           int64_t ld, double a, uint64_t seed, uint64_t step0, int64_t n_steps,
+                           int64_t thin, double* chain_dev, double* lnprob_dev, int64_t* n_accept_host,
+                           int mode, int plan);
+
 /* FP64 pipe peak (dependent-free DFMA streams on every SM); the roofline denominator.
  * Runs `reps` launches of `iters` FMA rounds, returns the best TFLOP/s and its time. */
 int stn_fp64_peak(int device, int iters, int reps, double* tflops, double* ms);

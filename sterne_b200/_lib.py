@@ -101,6 +101,10 @@ SYMBOLS = [
     ('stn_ipc_export', _int, [_vp, _vp]),
     ('stn_ipc_open', _int, [_int, _vp, ctypes.POINTER(_vp)]),
     ('stn_ipc_close', _int, [_int, _vp]),
+    ('stn_multi_set_prior', _int, [_vp, ctypes.POINTER(StnPrior)]),
+    ('stn_multi_ensemble_run', _int, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i64, _i64, ctypes.c_double,
+                                      ctypes.c_uint64, ctypes.c_uint64, _i64, _i64, _vp, _vp, ctypes.POINTER(_i64), _int,
+                                      _int]),
     ('stn_ensemble_run', _int, [_vp, _vp, _vp, _i64, _i64, ctypes.c_double, ctypes.c_uint64, ctypes.c_uint64, _i64, _i64,
                                 _vp, _vp, _vp, _int, _int, _int, _vp]),
 ]

@@ -946,6 +946,66 @@ stn_stretch_accept_kernel(double* __restrict__ x, double* __restrict__ lp, const
     if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(n_accept, (unsigned long long)__popc(ballot));
 }
 
+// Walker-sharded forms of the two stretch kernels (several GPUs, one ensemble): this device proposes for
+// the proposals [k0, k0 + cnt) of the half-step from ITS copy of the walkers, and the accept kernel
+// stores every accepted walker into the copies of ALL devices (peer-mapped pointers: the exchange of
+// the updated half over NVLink is the kernel's own stores).  Philox counters are global walker
+// indices, so the chain does not depend on how many devices share the ensemble.
+struct WalkerCopies {
+    double* x[STN_MAX_OUTS];
+    double* lp[STN_MAX_OUTS];
+    int n;
+};
+
+__global__ void __launch_bounds__(kThreads)
+stn_stretch_propose_part_kernel(const double* __restrict__ x, const int64_t W, const int P, const int64_t ld,
+                                const int half, const double a, const uint64_t seed, const uint64_t step,
+                                const int64_t k0, const int64_t cnt, double* __restrict__ y, double* __restrict__ z_out) {
+    const int64_t H = W / 2;
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= cnt) return;
+    const int64_t k = k0 + q;
+    uint32_t r[4];
+    philox4x32_10((uint32_t)k, (uint32_t)(k >> 32), (uint32_t)step, (uint32_t)(step >> 32) ^ (half ? 0x80000000u : 0u),
+                  (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    const double u = u01(r[0], r[1]);
+    const double t = (a - 1.0) * u + 1.0;
+    const double z = t * t / a;
+    const int64_t j = (int64_t)(u01(r[2], r[3]) * (double)H);
+    const double* xi = x + (half ? H + k : k) * ld;
+    const double* xj = x + (half ? j : H + j) * ld;
+    for (int p = 0; p < P; ++p) y[q * P + p] = fma(z, xi[p] - xj[p], xj[p]);
+    z_out[q] = z;
+}
+
+__global__ void __launch_bounds__(kThreads)
+stn_stretch_accept_part_kernel(const WalkerCopies C, const int64_t W, const int P, const int64_t ld, const int half,
+                               const uint64_t seed, const uint64_t step, const int64_t k0, const int64_t cnt,
+                               const double* __restrict__ y, const double* __restrict__ z,
+                               const double* __restrict__ lpy, unsigned long long* __restrict__ n_accept) {
+    const int64_t H = W / 2;
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool acc = false;
+    if (q < cnt) {
+        const int64_t k = k0 + q;
+        uint32_t r[4];
+        philox4x32_10((uint32_t)k, (uint32_t)(k >> 32), (uint32_t)step,
+                      (uint32_t)(step >> 32) ^ (half ? 0xC0000000u : 0x40000000u), (uint32_t)seed,
+                      (uint32_t)(seed >> 32), r);
+        const int64_t i = half ? H + k : k;
+        const double lnq = (double)(P - 1) * log(z[q]) + lpy[q] - C.lp[0][i];
+        acc = (lpy[q] > -CUDART_INF) && (lpy[q] == lpy[q]) && (log(u01(r[0], r[1])) < lnq);
+        if (acc) {
+            for (int c = 0; c < C.n; ++c) {
+                for (int p = 0; p < P; ++p) C.x[c][i * ld + p] = y[q * P + p];
+                C.lp[c][i] = lpy[q];
+            }
+        }
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, acc);
+    if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(n_accept, (unsigned long long)__popc(ballot));
+}
+
 // ---------------------------------------------------------------------------------
 // Fused ensemble sampler: the WHOLE stretch-move loop in one persistent cooperative kernel.
 // Per half-step every thread proposes for its walkers, evaluates log prior + log L of the
@@ -1191,6 +1251,8 @@ struct StnCtx {
     int64_t gather_elems = 0;
     double* sampler_buf = nullptr;      // stn_ensemble_run (three-launch engine): proposals, stretch factors, log-posteriors
     int64_t sampler_elems = 0;
+    cudaEvent_t sampler_ev[2] = {};     // stn_multi_ensemble_run: "this device finished half-step h" (ping-pong)
+    unsigned long long* sampler_nacc = nullptr;
 };
 
 // Several contexts of the same problem, one per device, driven as one (stn_multi_*).
@@ -1809,6 +1871,9 @@ int stn_destroy(StnCtx* ctx) {
     }
     if (ctx->gather_buf) cudaFree(ctx->gather_buf);
     if (ctx->sampler_buf) cudaFree(ctx->sampler_buf);
+    if (ctx->sampler_nacc) cudaFree(ctx->sampler_nacc);
+    for (int i = 0; i < 2; ++i)
+        if (ctx->sampler_ev[i]) cudaEventDestroy(ctx->sampler_ev[i]);
     if (ctx->timing_stream) cudaStreamDestroy(ctx->timing_stream);
     delete ctx;
     return STN_OK;
@@ -2173,6 +2238,141 @@ int stn_multi_loglike_dev(StnMulti* m, const double* const* theta_dev, const int
     return rc;
 }
 
+int stn_multi_set_prior(StnMulti* m, const StnPrior* prior) {
+    if (!m || m->ctx.empty()) return fail(STN_ERR_INVALID, "null multi-context");
+    for (StnCtx* c : m->ctx) {
+        const int rc = stn_set_prior(c, prior);
+        if (rc) return rc;
+    }
+    return STN_OK;
+}
+
+int stn_multi_ensemble_run(StnMulti* m, double* const* x_dev, double* const* lp_dev, int64_t n_walkers, int64_t ld,
+                           double a, uint64_t seed, uint64_t step0, int64_t n_steps, int64_t thin, double* chain_dev,
+                           double* lnprob_dev, int64_t* n_accept_host, int mode, int plan) {
+    if (!m || m->ctx.empty() || !x_dev || !lp_dev) return fail(STN_ERR_INVALID, "null argument");
+    const int G = (int)m->ctx.size();
+    if (G > STN_MAX_OUTS) return fail(STN_ERR_INVALID, "at most %d devices can share one ensemble", STN_MAX_OUTS);
+    const int P = m->ctx[0]->prob.n_params;
+    if (n_walkers < 2 || (n_walkers & 1) || ld < P || !(a > 1.0) || n_steps < 0 || thin < 1)
+        return fail(STN_ERR_INVALID, "stretch move needs an even number of walkers >= 2, ld >= P, a > 1, thin >= 1");
+    if (mode != STN_MODE_FAST && mode != STN_MODE_STRICT) return fail(STN_ERR_INVALID, "bad mode %d", mode);
+    for (int g = 0; g < G; ++g) {
+        if (!m->ctx[g]->has_prior) return fail(STN_ERR_INVALID, "stn_multi_ensemble_run needs stn_multi_set_prior first");
+        if (!x_dev[g] || !lp_dev[g]) return fail(STN_ERR_INVALID, "null walker copy %d", g);
+        for (int b = 0; b < G; ++b)
+            if (!m->peer_ok[(size_t)g * G + b])
+                return fail(STN_ERR_DEVICE, "devices %d and %d have no peer access", m->ctx[g]->device, m->ctx[b]->device);
+    }
+    const int64_t H = n_walkers / 2;
+    if (plan == 0) plan = make_plan(1, 1);              // one summation order whatever the number of devices
+    // per device: proposal range of a half-step, scratch, events, acceptance counter
+    std::vector<int64_t> k0(G), cnt(G);
+    for (int g = 0; g < G; ++g) {
+        int64_t lo, hi;
+        stn_multi_slice(H, G, g, &lo, &hi);
+        k0[g] = lo;
+        cnt[g] = hi - lo;
+        StnCtx* c = m->ctx[g];
+        STN_CUDA(cudaSetDevice(c->device));
+        int rc = host_pipe_init(c);
+        if (rc) return rc;
+        const int64_t need = cnt[g] * P + 2 * cnt[g] + 1;
+        if (c->sampler_elems < need) {
+            STN_CUDA(cudaDeviceSynchronize());
+            if (c->sampler_buf) cudaFree(c->sampler_buf);
+            c->sampler_buf = nullptr;
+            c->sampler_elems = 0;
+            STN_CUDA(cudaMalloc(&c->sampler_buf, (size_t)need * sizeof(double)));
+            c->sampler_elems = need;
+        }
+        for (int i = 0; i < 2; ++i)
+            if (!c->sampler_ev[i]) STN_CUDA(cudaEventCreateWithFlags(&c->sampler_ev[i], cudaEventDisableTiming));
+        if (!c->sampler_nacc) STN_CUDA(cudaMalloc(&c->sampler_nacc, sizeof(unsigned long long)));
+        STN_CUDA(cudaMemsetAsync(c->sampler_nacc, 0, sizeof(unsigned long long), c->streams[0]));
+    }
+    auto body = [&]() -> int {
+        int64_t hs = 0;                                  // running half-step number (event ping-pong)
+        for (int64_t t = 0; t < n_steps; ++t) {
+            for (int half = 0; half < 2; ++half, ++hs) {
+                for (int g = 0; g < G; ++g) {
+                    StnCtx* c = m->ctx[g];
+                    STN_CUDA(cudaSetDevice(c->device));
+                    cudaStream_t st = c->streams[0];
+                    // every device must have finished the previous half-step: its accepted walkers are in this
+                    // device's copy, and it no longer reads the rows this half-step overwrites
+                    if (hs > 0)
+                        for (int b = 0; b < G; ++b)
+                            if (b != g) STN_CUDA(cudaStreamWaitEvent(st, m->ctx[b]->sampler_ev[(hs - 1) & 1], 0));
+                    if (cnt[g] == 0) {
+                        STN_CUDA(cudaEventRecord(c->sampler_ev[hs & 1], st));
+                        continue;
+                    }
+                    double* y = c->sampler_buf;
+                    double* z = y + cnt[g] * P;
+                    double* lpy = z + cnt[g];
+                    const unsigned grid = (unsigned)((cnt[g] + kThreads - 1) / kThreads);
+                    (void)cudaGetLastError();
+                    stn_stretch_propose_part_kernel<<<grid, kThreads, 0, st>>>(x_dev[g], n_walkers, P, ld, half, a, seed,
+                                                                               step0 + (uint64_t)t, k0[g], cnt[g], y, z);
+                    STN_CUDA(cudaGetLastError());
+                    int rc = launch_loglike(c, y, cnt[g], P, STN_LAYOUT_AOS, mode, plan, lpy, st, 1, 1);
+                    if (rc) return rc;
+                    WalkerCopies C;
+                    C.n = G;
+                    C.x[0] = x_dev[g];                   // own copy first: it also supplies the current log-posterior
+                    C.lp[0] = lp_dev[g];
+                    for (int b = 0, o = 1; b < G; ++b)
+                        if (b != g) {
+                            C.x[o] = x_dev[b];
+                            C.lp[o] = lp_dev[b];
+                            ++o;
+                        }
+                    stn_stretch_accept_part_kernel<<<grid, kThreads, 0, st>>>(C, n_walkers, P, ld, half, seed,
+                                                                              step0 + (uint64_t)t, k0[g], cnt[g], y, z, lpy,
+                                                                              c->sampler_nacc);
+                    STN_CUDA(cudaGetLastError());
+                    c->launches += 2;
+                    STN_CUDA(cudaEventRecord(c->sampler_ev[hs & 1], st));
+                }
+            }
+            if (chain_dev && (t + 1) % thin == 0) {
+                // device 0's copy is complete once every device's last half-step has landed
+                StnCtx* c = m->ctx[0];
+                STN_CUDA(cudaSetDevice(c->device));
+                cudaStream_t st = c->streams[0];
+                for (int b = 1; b < G; ++b) STN_CUDA(cudaStreamWaitEvent(st, m->ctx[b]->sampler_ev[(hs - 1) & 1], 0));
+                const int64_t slot = (t + 1) / thin - 1;
+                STN_CUDA(cudaMemcpy2DAsync(chain_dev + slot * n_walkers * P, (size_t)P * sizeof(double), x_dev[0],
+                                           (size_t)ld * sizeof(double), (size_t)P * sizeof(double), (size_t)n_walkers,
+                                           cudaMemcpyDeviceToDevice, st));
+                if (lnprob_dev)
+                    STN_CUDA(cudaMemcpyAsync(lnprob_dev + slot * n_walkers, lp_dev[0], (size_t)n_walkers * sizeof(double),
+                                             cudaMemcpyDeviceToDevice, st));
+                // the next half-step of the OTHER devices overwrites rows of device 0's copy: they wait for this copy
+                STN_CUDA(cudaEventRecord(c->sampler_ev[(hs - 1) & 1], st));
+            }
+        }
+        return STN_OK;
+    };
+    int rc = body();
+    // synchronous on return (also after an error); acceptances summed over the devices
+    unsigned long long total = 0;
+    for (int g = 0; g < G; ++g) {
+        StnCtx* c = m->ctx[g];
+        cudaSetDevice(c->device);
+        if (c->streams[0]) {
+            const cudaError_t e = cudaStreamSynchronize(c->streams[0]);
+            if (e != cudaSuccess && !rc) rc = fail(STN_ERR_CUDA, "device %d: %s", c->device, cudaGetErrorString(e));
+        }
+        unsigned long long v = 0;
+        if (!rc && c->sampler_nacc && cudaMemcpy(&v, c->sampler_nacc, sizeof(v), cudaMemcpyDeviceToHost) == cudaSuccess) total += v;
+    }
+    cudaSetDevice(m->ctx[0]->device);
+    if (!rc && n_accept_host) *n_accept_host += (int64_t)total;
+    return rc;
+}
+
 int stn_host_register(void* ptr, int64_t bytes) {
     if (!ptr || bytes <= 0) return fail(STN_ERR_INVALID, "bad argument");
     STN_CUDA(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
@@ -2332,6 +2532,9 @@ int stn_ensemble_run(StnCtx* ctx, double* x_dev, double* lp_dev, int64_t n_walke
     if (ctx->sampler_elems < need) {
         STN_CUDA(cudaStreamSynchronize(st));
         if (ctx->sampler_buf) cudaFree(ctx->sampler_buf);
+    if (ctx->sampler_nacc) cudaFree(ctx->sampler_nacc);
+    for (int i = 0; i < 2; ++i)
+        if (ctx->sampler_ev[i]) cudaEventDestroy(ctx->sampler_ev[i]);
         ctx->sampler_buf = nullptr;
         ctx->sampler_elems = 0;
         STN_CUDA(cudaMalloc(&ctx->sampler_buf, (size_t)need * sizeof(double)));

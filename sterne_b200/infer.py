@@ -50,6 +50,8 @@ def default_shares(n, efac):
 def run(refepoch, initsfile, pmparin, parfile, *args, shares=None, pmparin_preliminaries=None,
         a1dot_constraints=False, nwalkers=1024, iterations=1000, burn=None, thin=1, outdir='outdir',
         earth_provider=None, earth_xyz=None, device=0, seed=0, init_scale=1e-3):
+    """device: a CUDA ordinal, or a list of them -- the ensemble is then shared among those GPUs of this
+    box from this one process (FusedEnsembleSampler / stn_multi_ensemble_run), same chain as on one GPU."""
     if not os.path.exists(initsfile):
         raise FileNotFoundError('%s does not exist' % initsfile)
     pmparins, parfiles = split_args(pmparin, parfile, *args)
@@ -105,12 +107,12 @@ def main(argv=None):
     ap.add_argument('--nwalkers', type=int, default=1024)
     ap.add_argument('--iterations', type=int, default=1000)
     ap.add_argument('--outdir', default='outdir')
-    ap.add_argument('--device', type=int, default=0)
+    ap.add_argument('--device', type=int, nargs='+', default=[0], help='CUDA ordinal(s); several share the ensemble')
     ap.add_argument('--seed', type=int, default=0)
     a = ap.parse_args(argv)
     res = run(a.refepoch, a.initsfile, *a.files, shares=a.shares, pmparin_preliminaries=a.preliminaries,
               a1dot_constraints=a.a1dot_constraints, nwalkers=a.nwalkers, iterations=a.iterations, outdir=a.outdir,
-              device=a.device, seed=a.seed)
+              device=a.device if len(a.device) > 1 else a.device[0], seed=a.seed)
     print(open(res['estimates']).read())
     return 0
 

@@ -181,6 +181,28 @@ class CompiledProblem(object):
         return int(sum(src['n_epochs'] for src in self.sources))
 
 
+def prior_as_ctypes(prior, names):
+    """(StnPrior, keepalive) of a sampler.BoxPrior whose keys are the context's column order."""
+    if list(prior.keys) != list(names):
+        raise ValueError('prior keys %r differ from the context column order %r' % (prior.keys, names))
+    kind = np.array([_lib.PRIOR_KINDS[k] for k in prior.kinds], dtype=np.int32)
+    a = np.ascontiguousarray(prior.a, dtype=np.float64)
+    b = np.ascontiguousarray(prior.b, dtype=np.float64)
+    col = np.array([c for c, _, _ in prior.sin_limits], dtype=np.int32)
+    lo = np.array([l for _, l, _ in prior.sin_limits], dtype=np.float64)
+    hi = np.array([h for _, _, h in prior.sin_limits], dtype=np.float64)
+    pr = _lib.StnPrior()
+    pr.n_params = len(kind)
+    pr.kind = kind.ctypes.data_as(_lib.c_int32_p)
+    pr.a = a.ctypes.data_as(_lib.c_double_p)
+    pr.b = b.ctypes.data_as(_lib.c_double_p)
+    pr.n_sin_limits = len(col)
+    pr.sin_col = col.ctypes.data_as(_lib.c_int32_p)
+    pr.sin_lo = lo.ctypes.data_as(_lib.c_double_p)
+    pr.sin_hi = hi.ctypes.data_as(_lib.c_double_p)
+    return pr, (kind, a, b, col, lo, hi)
+
+
 class DeviceContext(object):
     """Owns one StnCtx (device copies of a CompiledProblem)."""
 
@@ -219,26 +241,9 @@ class DeviceContext(object):
 
     def set_prior(self, prior):
         """prior: sampler.BoxPrior whose keys are this context's column order."""
-        import numpy as np
-        if list(prior.keys) != list(self.problem.names):
-            raise ValueError('prior keys %r differ from the context column order %r'
-                             % (prior.keys, self.problem.names))
-        kind = np.array([_lib.PRIOR_KINDS[k] for k in prior.kinds], dtype=np.int32)
-        a = np.ascontiguousarray(prior.a, dtype=np.float64)
-        b = np.ascontiguousarray(prior.b, dtype=np.float64)
-        col = np.array([c for c, _, _ in prior.sin_limits], dtype=np.int32)
-        lo = np.array([l for _, l, _ in prior.sin_limits], dtype=np.float64)
-        hi = np.array([h for _, _, h in prior.sin_limits], dtype=np.float64)
-        pr = _lib.StnPrior()
-        pr.n_params = len(kind)
-        pr.kind = kind.ctypes.data_as(_lib.c_int32_p)
-        pr.a = a.ctypes.data_as(_lib.c_double_p)
-        pr.b = b.ctypes.data_as(_lib.c_double_p)
-        pr.n_sin_limits = len(col)
-        pr.sin_col = col.ctypes.data_as(_lib.c_int32_p)
-        pr.sin_lo = lo.ctypes.data_as(_lib.c_double_p)
-        pr.sin_hi = hi.ctypes.data_as(_lib.c_double_p)
+        pr, keep = prior_as_ctypes(prior, self.problem.names)
         _lib.check(self.lib.stn_set_prior(self.handle, ctypes.byref(pr)))
+        del keep
         self.prior = prior
 
     def logpost_ptr(self, theta_ptr, n, ld, layout, mode, plan, out_ptr, stream=0):
@@ -285,6 +290,7 @@ class MultiDeviceContext(object):
         _lib.check(self.lib.stn_multi_create(ctypes.byref(pb), arr, len(self.devices), ctypes.byref(handle)))
         del keep
         self.handle = handle
+        self.prior = None
 
     def close(self):
         if getattr(self, 'handle', None):
@@ -315,6 +321,23 @@ class MultiDeviceContext(object):
 
     def loglike_host_ptr(self, theta_ptr, n, ld, layout, mode, plan, out_ptr):
         _lib.check(self.lib.stn_multi_loglike_host(self.handle, theta_ptr, n, ld, layout, mode, plan, out_ptr))
+
+    def set_prior(self, prior):
+        pr, keep = prior_as_ctypes(prior, self.problem.names)
+        _lib.check(self.lib.stn_multi_set_prior(self.handle, ctypes.byref(pr)))
+        del keep
+        self.prior = prior
+
+    def ensemble_run(self, x_ptrs, lp_ptrs, n_walkers, ld, a, seed, step0, n_steps, thin, chain_ptr, lnprob_ptr,
+                     mode, plan):
+        """stn_multi_ensemble_run; returns the number of acceptances of this call."""
+        G = len(self.devices)
+        xs = (ctypes.c_void_p * G)(*[ctypes.c_void_p(int(p)) for p in x_ptrs])
+        ls = (ctypes.c_void_p * G)(*[ctypes.c_void_p(int(p)) for p in lp_ptrs])
+        nacc = ctypes.c_int64(0)
+        _lib.check(self.lib.stn_multi_ensemble_run(self.handle, xs, ls, n_walkers, ld, a, seed, step0, n_steps, thin,
+                                                   chain_ptr, lnprob_ptr, ctypes.byref(nacc), mode, plan))
+        return nacc.value
 
     def loglike_dev_ptrs(self, theta_ptrs, counts, ld, layout, mode, plan, out_ptr, out_device):
         G = len(self.devices)

@@ -274,11 +274,19 @@ class FusedEnsembleSampler(object):
     throughput kernel, three launches per half-step issued from C.  'persistent' / 'launches' force one.
     Random numbers are counter-based (Philox keyed by `seed`): a run is reproducible, independent of
     launch geometry and of the engine.  Columns of p0 / chain follow prior.keys.
+
+    A likelihood built with a device LIST shares the ensemble among those GPUs (devices=None: the
+    likelihood's list; stn_multi_ensemble_run): every GPU keeps a full copy of the walkers, evaluates its
+    slice of each half-step's proposals with the throughput kernel and its accept kernel stores the
+    accepted walkers into all copies over NVLink.  Same chain, bit for bit, as on one GPU.  Worth it for
+    long series x large ensembles (>= ~1 ms of likelihood work per half-step); short series are
+    latency-bound and run best as the one-GPU persistent kernel (devices=[d]).
     """
 
     ENGINES = {'auto': 0, 'persistent': 1, 'launches': 2}
 
-    def __init__(self, likelihood, prior, nwalkers, a=2.0, seed=0, mode=None, plan=None, engine='auto'):
+    def __init__(self, likelihood, prior, nwalkers, a=2.0, seed=0, mode=None, plan=None, engine='auto',
+                 devices=None):
         import torch
         from . import _lib
         ndim = prior.ndim
@@ -290,9 +298,17 @@ class FusedEnsembleSampler(object):
         self.like, self.prior = likelihood, prior
         self.nwalkers, self.ndim, self.a, self.seed = nwalkers, ndim, float(a), int(seed)
         self.device = torch.device('cuda', likelihood.device)
+        self.devices = list(likelihood.devices) if devices is None else [int(d) for d in devices]
         self.ctx = likelihood._context(prior.keys)
         if self.ctx.prior is not prior:
             self.ctx.set_prior(prior)
+        self.multi = None
+        if len(self.devices) > 1:
+            if self.devices != list(likelihood.devices):
+                raise ValueError('devices must be the likelihood\'s device list %r' % (likelihood.devices,))
+            self.multi = likelihood._multi(prior.keys)
+            if self.multi.prior is not prior:
+                self.multi.set_prior(prior)
         self.mode = likelihood.mode if mode is None else _lib.MODES[mode]
         # lanes = 1, splits = 1 is the summation order of the persistent kernel; the launch engine uses the
         # same plan unless told otherwise, so both engines give the same chain
@@ -324,9 +340,19 @@ class FusedEnsembleSampler(object):
             self.lnprob = torch.empty((nkeep, W), dtype=torch.float64, device=dev)
             if nkeep:
                 chain_ptr, lnprob_ptr = self.chain.data_ptr(), self.lnprob.data_ptr()
-        self.check(self.lib.stn_ensemble_run(self.ctx.handle, x.data_ptr(), lp.data_ptr(), W, P, self.a, self.seed,
-                                             self.step, nsteps, thin, chain_ptr, lnprob_ptr, self._nacc.data_ptr(),
-                                             self.mode, self.plan, self.engine, stream))
+        if self.multi is not None:
+            torch.cuda.synchronize(dev)
+            xs = [x] + [x.to(torch.device('cuda', d)) for d in self.devices[1:]]
+            lps = [lp] + [lp.to(torch.device('cuda', d)) for d in self.devices[1:]]
+            for d in self.devices:
+                torch.cuda.synchronize(d)
+            self._nacc_multi = getattr(self, '_nacc_multi', 0) + self.multi.ensemble_run(
+                [t.data_ptr() for t in xs], [t.data_ptr() for t in lps], W, P, self.a, self.seed, self.step, nsteps, thin,
+                chain_ptr, lnprob_ptr, self.mode, self.plan)
+        else:
+            self.check(self.lib.stn_ensemble_run(self.ctx.handle, x.data_ptr(), lp.data_ptr(), W, P, self.a, self.seed,
+                                                 self.step, nsteps, thin, chain_ptr, lnprob_ptr, self._nacc.data_ptr(),
+                                                 self.mode, self.plan, self.engine, stream))
         self.step += nsteps
         self.nproposed += W * nsteps
         self.last = (x, lp)
@@ -334,4 +360,4 @@ class FusedEnsembleSampler(object):
 
     @property
     def acceptance_fraction(self):
-        return float(self._nacc.item()) / max(self.nproposed, 1)
+        return (float(self._nacc.item()) + getattr(self, '_nacc_multi', 0)) / max(self.nproposed, 1)

@@ -223,3 +223,35 @@ def test_fused_sampler_matches_torch_sampler_statistically():
     assert 0.02 < a3.acceptance_fraction < 0.98
     like3.close()
     like.close()
+
+
+@pytest.mark.gpu
+def test_ensemble_shared_by_several_devices_gives_the_same_chain():
+    """stn_multi_ensemble_run: the walkers of one ensemble are shared among several contexts / GPUs (every
+    device proposes and evaluates its slice of a half-step, its accept kernel writes into all copies);
+    the chain is bit-identical to the one-GPU run.  [0, 0] exercises it on a single-GPU box."""
+    from sterne_b200.sampler import FusedEnsembleSampler
+    case = synthetic.config5('C', n_epochs=200)
+    limits = {k: [case.box[k][0], case.box[k][1], 'Uniform'] for k in case.names}
+    prior = BoxPrior(limits)
+    nw = 1000
+    half = np.array([0.5 * (case.box[k][1] - case.box[k][0]) for k in case.names])
+    p0 = case.truth_vector() + 0.02 * half * np.random.default_rng(3).standard_normal((nw, case.n_params))
+    one = case.likelihood(device=0)
+    ref = FusedEnsembleSampler(one, prior, nw, seed=5, engine='launches')
+    ref.run(p0, 12, thin=3)
+    lists = [[0, 0], [0, 0, 0]]
+    if torch.cuda.device_count() >= 2:
+        lists.append(list(range(min(torch.cuda.device_count(), 8))))
+    for devices in lists:
+        like = case.likelihood(device=devices)
+        s = FusedEnsembleSampler(like, prior, nw, seed=5)
+        s.run(p0, 12, thin=3)
+        assert torch.equal(s.chain, ref.chain) and torch.equal(s.lnprob, ref.lnprob), devices
+        assert torch.equal(s.last[0], ref.last[0]) and torch.equal(s.last[1], ref.last[1])
+        assert s.acceptance_fraction == ref.acceptance_fraction
+        s.run(s.last[0], 5, store=False)                       # continuing works (step counter, fresh copies)
+        like.close()
+    ref.run(ref.last[0], 5, store=False)
+    assert torch.equal(s.last[0], ref.last[0])
+    one.close()
