@@ -520,7 +520,7 @@ def run_ours(args, rank, local_rank, world):
                 # command, read from the committed summary named in traffic_source; algorithmic bytes per launch below
                 'traffic': traffic, 'traffic_unit': 'bytes per launch', 'traffic_source': traffic_file,
                 'algorithmic_bytes': alg_bytes,
-                'kernel': 'stn_loglike_fast_kernel<3,1>', 'kernel_ms': kernel_ms,
+                'kernel': 'stn_loglike_fast_kernel<3,1,64>', 'kernel_ms': kernel_ms,
                 'flops_per_eval': FLOPS_PER_EVAL['C'],
                 'peak_source': 'stn_fp64_peak DFMA micro-benchmark in this run (MEASURED_PEAKS.json has no FP64 '
                                'figure); nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2',

@@ -418,6 +418,11 @@ def test_large_batch_against_the_c_oracle():
     got = like.log_likelihood_batch(theta)
     err = logl_err(got, want, logl_scale(case.LoD_VLBI))
     assert err.max() < LOGL_RTOL, (err.max(), int((err > LOGL_RTOL).sum()))
+    # pure relative error, exceedances (log L crossing zero among 2^15 vectors) arbitrated in 50-digit arithmetic
+    floor = logl_scale(case.LoD_VLBI)
+    stats = mp_arbiter.parity_stats(case, theta, got, want, rtol=LOGL_RTOL, floor=floor, max_arbitrated=6, noise_sample=6)
+    record_parity('config5_C/fast/32768_vs_c_oracle', stats)
+    assert stats['explained'], stats
     like.close()
 
 
