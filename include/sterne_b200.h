@@ -253,8 +253,9 @@ int stn_multi_loglike_dev(StnMulti* m, const double* const* theta_dev, const int
  * log-posteriors).  In each half-step device g proposes and evaluates the proposals of its slice of the
  * half, and its accept kernel stores the accepted walkers into EVERY device's copy through peer-mapped
  * pointers -- the exchange of the updated half over NVLink is fused into the kernel; the devices are
- * ordered by events, not by the host.  Random numbers are keyed by global walker indices and the plan
- * defaults to lanes = 1 | splits = 1, so the chain is bit-identical to stn_ensemble_run's on one device.
+ * ordered by events, not by the host.  Random numbers are keyed by global walker indices and plan = 0
+ * is the plan of the WHOLE half-ensemble (stn_auto_plan(W / 2)), so the chain is bit-identical to
+ * stn_ensemble_run's launch engine on one device, whatever the number of devices.
  * chain_dev / lnprob_dev (nullable) live on the first device; *n_accept_host is incremented.  Needs
  * stn_multi_set_prior and peer access between all devices (STN_ERR_DEVICE otherwise).  Synchronous. */
 int stn_multi_set_prior(StnMulti* m, const StnPrior* prior);

@@ -35,6 +35,7 @@
 #else
 #define STN_ASSERT(x) ((void)0)
 #endif
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstdarg>
@@ -1004,6 +1005,33 @@ stn_stretch_accept_part_kernel(const WalkerCopies C, const int64_t W, const int 
     }
     const unsigned ballot = __ballot_sync(0xffffffffu, acc);
     if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(n_accept, (unsigned long long)__popc(ballot));
+}
+
+// After a half-step, this device's slice of the updated half -- rows [row0, row0 + cnt) of x and of lp, a
+// contiguous block -- goes to every other device's copy with coalesced 16-byte stores over NVLink
+// (peer-mapped pointers; scattered 8-byte peer stores from the accept kernel itself were 3x slower).
+__global__ void __launch_bounds__(kThreads)
+stn_broadcast_rows_kernel(const WalkerCopies C, const int64_t row0, const int64_t cnt, const int64_t ld) {
+    const int64_t nx = cnt * ld, stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const double* sx = C.x[0] + row0 * ld;
+    const double* sl = C.lp[0] + row0;
+    if ((((uintptr_t)sx) & 15) == 0 && (nx & 1) == 0) {
+        const double2* s2 = reinterpret_cast<const double2*>(sx);
+        for (int64_t e = t0; e < nx / 2; e += stride) {
+            const double2 v = s2[e];
+            for (int c = 1; c < C.n; ++c) reinterpret_cast<double2*>(C.x[c] + row0 * ld)[e] = v;
+        }
+    } else {
+        for (int64_t e = t0; e < nx; e += stride) {
+            const double v = sx[e];
+            for (int c = 1; c < C.n; ++c) C.x[c][row0 * ld + e] = v;
+        }
+    }
+    for (int64_t e = t0; e < cnt; e += stride) {
+        const double v = sl[e];
+        for (int c = 1; c < C.n; ++c) C.lp[c][row0 + e] = v;
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -2265,7 +2293,7 @@ int stn_multi_ensemble_run(StnMulti* m, double* const* x_dev, double* const* lp_
                 return fail(STN_ERR_DEVICE, "devices %d and %d have no peer access", m->ctx[g]->device, m->ctx[b]->device);
     }
     const int64_t H = n_walkers / 2;
-    if (plan == 0) plan = make_plan(1, 1);              // one summation order whatever the number of devices
+    if (plan == 0) plan = pick_plan(m->ctx[0], H);      // from the WHOLE half-ensemble: one summation order whatever the number of devices
     // per device: proposal range of a half-step, scratch, events, acceptance counter
     std::vector<int64_t> k0(G), cnt(G);
     for (int g = 0; g < G; ++g) {
@@ -2291,71 +2319,134 @@ int stn_multi_ensemble_run(StnMulti* m, double* const* x_dev, double* const* lp_
         if (!c->sampler_nacc) STN_CUDA(cudaMalloc(&c->sampler_nacc, sizeof(unsigned long long)));
         STN_CUDA(cudaMemsetAsync(c->sampler_nacc, 0, sizeof(unsigned long long), c->streams[0]));
     }
-    auto body = [&]() -> int {
-        int64_t hs = 0;                                  // running half-step number (event ping-pong)
-        for (int64_t t = 0; t < n_steps; ++t) {
-            for (int half = 0; half < 2; ++half, ++hs) {
-                for (int g = 0; g < G; ++g) {
-                    StnCtx* c = m->ctx[g];
-                    STN_CUDA(cudaSetDevice(c->device));
-                    cudaStream_t st = c->streams[0];
-                    // every device must have finished the previous half-step: its accepted walkers are in this
-                    // device's copy, and it no longer reads the rows this half-step overwrites
-                    if (hs > 0)
-                        for (int b = 0; b < G; ++b)
-                            if (b != g) STN_CUDA(cudaStreamWaitEvent(st, m->ctx[b]->sampler_ev[(hs - 1) & 1], 0));
-                    if (cnt[g] == 0) {
-                        STN_CUDA(cudaEventRecord(c->sampler_ev[hs & 1], st));
-                        continue;
-                    }
-                    double* y = c->sampler_buf;
-                    double* z = y + cnt[g] * P;
-                    double* lpy = z + cnt[g];
-                    const unsigned grid = (unsigned)((cnt[g] + kThreads - 1) / kThreads);
-                    (void)cudaGetLastError();
-                    stn_stretch_propose_part_kernel<<<grid, kThreads, 0, st>>>(x_dev[g], n_walkers, P, ld, half, a, seed,
-                                                                               step0 + (uint64_t)t, k0[g], cnt[g], y, z);
-                    STN_CUDA(cudaGetLastError());
-                    int rc = launch_loglike(c, y, cnt[g], P, STN_LAYOUT_AOS, mode, plan, lpy, st, 1, 1);
-                    if (rc) return rc;
-                    WalkerCopies C;
-                    C.n = G;
-                    C.x[0] = x_dev[g];                   // own copy first: it also supplies the current log-posterior
-                    C.lp[0] = lp_dev[g];
-                    for (int b = 0, o = 1; b < G; ++b)
-                        if (b != g) {
-                            C.x[o] = x_dev[b];
-                            C.lp[o] = lp_dev[b];
-                            ++o;
-                        }
-                    stn_stretch_accept_part_kernel<<<grid, kThreads, 0, st>>>(C, n_walkers, P, ld, half, seed,
-                                                                              step0 + (uint64_t)t, k0[g], cnt[g], y, z, lpy,
-                                                                              c->sampler_nacc);
-                    STN_CUDA(cudaGetLastError());
-                    c->launches += 2;
-                    STN_CUDA(cudaEventRecord(c->sampler_ev[hs & 1], st));
-                }
-            }
-            if (chain_dev && (t + 1) % thin == 0) {
-                // device 0's copy is complete once every device's last half-step has landed
-                StnCtx* c = m->ctx[0];
-                STN_CUDA(cudaSetDevice(c->device));
-                cudaStream_t st = c->streams[0];
-                for (int b = 1; b < G; ++b) STN_CUDA(cudaStreamWaitEvent(st, m->ctx[b]->sampler_ev[(hs - 1) & 1], 0));
-                const int64_t slot = (t + 1) / thin - 1;
-                STN_CUDA(cudaMemcpy2DAsync(chain_dev + slot * n_walkers * P, (size_t)P * sizeof(double), x_dev[0],
-                                           (size_t)ld * sizeof(double), (size_t)P * sizeof(double), (size_t)n_walkers,
-                                           cudaMemcpyDeviceToDevice, st));
-                if (lnprob_dev)
-                    STN_CUDA(cudaMemcpyAsync(lnprob_dev + slot * n_walkers, lp_dev[0], (size_t)n_walkers * sizeof(double),
-                                             cudaMemcpyDeviceToDevice, st));
-                // the next half-step of the OTHER devices overwrites rows of device 0's copy: they wait for this copy
-                STN_CUDA(cudaEventRecord(c->sampler_ev[(hs - 1) & 1], st));
+    // One host thread per device issues that device's launches, so the per-half-step driver calls (three
+    // launches, G - 1 event waits, one record) of all devices run side by side instead of G-fold in series.
+    // The threads meet at a host barrier after every half-step: an event must have been RECORDED by its
+    // owner's thread before another thread makes its stream wait for it.
+    struct HostBarrier {
+        std::atomic<int> count{0};
+        std::atomic<int> gen{0};
+        int n;
+        explicit HostBarrier(int n_) : n(n_) {}
+        void wait() {
+            const int g = gen.load(std::memory_order_acquire);
+            if (count.fetch_add(1, std::memory_order_acq_rel) == n - 1) {
+                count.store(0, std::memory_order_relaxed);
+                gen.fetch_add(1, std::memory_order_release);
+            } else {
+                while (gen.load(std::memory_order_acquire) == g) std::this_thread::yield();
             }
         }
+    };
+    HostBarrier bar(G);
+    std::atomic<int> failed{0};
+    std::vector<int> rcs(G, STN_OK);
+    std::vector<std::string> errs(G);
+    auto half_step = [&](int g, int64_t t, int half, int64_t hs) -> int {
+        StnCtx* c = m->ctx[g];
+        cudaStream_t st = c->streams[0];
+        // every device must have finished the previous half-step: its accepted walkers are in this
+        // device's copy, and it no longer reads the rows this half-step overwrites
+        if (hs > 0)
+            for (int b = 0; b < G; ++b)
+                if (b != g) STN_CUDA(cudaStreamWaitEvent(st, m->ctx[b]->sampler_ev[(hs - 1) & 1], 0));
+        if (cnt[g] > 0) {
+            double* y = c->sampler_buf;
+            double* z = y + cnt[g] * P;
+            double* lpy = z + cnt[g];
+            const unsigned grid = (unsigned)((cnt[g] + kThreads - 1) / kThreads);
+            (void)cudaGetLastError();
+            stn_stretch_propose_part_kernel<<<grid, kThreads, 0, st>>>(x_dev[g], n_walkers, P, ld, half, a, seed,
+                                                                       step0 + (uint64_t)t, k0[g], cnt[g], y, z);
+            STN_CUDA(cudaGetLastError());
+            const int rc = launch_loglike(c, y, cnt[g], P, STN_LAYOUT_AOS, mode, plan, lpy, st, 1, 1);
+            if (rc) return rc;
+            WalkerCopies C;
+            C.n = G;
+            C.x[0] = x_dev[g];                   // own copy first: it also supplies the current log-posterior
+            C.lp[0] = lp_dev[g];
+            for (int b = 0, o = 1; b < G; ++b)
+                if (b != g) {
+                    C.x[o] = x_dev[b];
+                    C.lp[o] = lp_dev[b];
+                    ++o;
+                }
+            WalkerCopies own = C;
+            own.n = 1;                           // accept into the local copy ...
+            stn_stretch_accept_part_kernel<<<grid, kThreads, 0, st>>>(own, n_walkers, P, ld, half, seed, step0 + (uint64_t)t,
+                                                                      k0[g], cnt[g], y, z, lpy, c->sampler_nacc);
+            STN_CUDA(cudaGetLastError());
+            c->launches += 2;
+            if (G > 1) {                         // ... then the slice goes to all other copies, coalesced
+                const int64_t row0 = (half ? n_walkers / 2 : 0) + k0[g];
+                const int64_t work = cnt[g] * ld / 2 + 1;
+                const unsigned bg = (unsigned)((work + kThreads - 1) / kThreads < 4096 ? (work + kThreads - 1) / kThreads : 4096);
+                stn_broadcast_rows_kernel<<<bg, kThreads, 0, st>>>(C, row0, cnt[g], ld);
+                STN_CUDA(cudaGetLastError());
+                c->launches++;
+            }
+        }
+        STN_CUDA(cudaEventRecord(c->sampler_ev[hs & 1], st));
         return STN_OK;
     };
-    int rc = body();
+    auto store_chain = [&](int64_t t, int64_t hs) -> int {
+        // device 0's copy is complete once every device's last half-step has landed
+        StnCtx* c = m->ctx[0];
+        cudaStream_t st = c->streams[0];
+        for (int b = 1; b < G; ++b) STN_CUDA(cudaStreamWaitEvent(st, m->ctx[b]->sampler_ev[(hs - 1) & 1], 0));
+        const int64_t slot = (t + 1) / thin - 1;
+        STN_CUDA(cudaMemcpy2DAsync(chain_dev + slot * n_walkers * P, (size_t)P * sizeof(double), x_dev[0],
+                                   (size_t)ld * sizeof(double), (size_t)P * sizeof(double), (size_t)n_walkers,
+                                   cudaMemcpyDeviceToDevice, st));
+        if (lnprob_dev)
+            STN_CUDA(cudaMemcpyAsync(lnprob_dev + slot * n_walkers, lp_dev[0], (size_t)n_walkers * sizeof(double),
+                                     cudaMemcpyDeviceToDevice, st));
+        // the next half-step of the OTHER devices overwrites rows of device 0's copy: they wait for this copy
+        STN_CUDA(cudaEventRecord(c->sampler_ev[(hs - 1) & 1], st));
+        return STN_OK;
+    };
+    auto worker = [&](int g) {
+        if (cudaSetDevice(m->ctx[g]->device) != cudaSuccess) {
+            rcs[g] = STN_ERR_CUDA;
+            errs[g] = "cudaSetDevice failed";
+            failed.store(1);
+        }
+        int64_t hs = 0;
+        for (int64_t t = 0; t < n_steps; ++t) {
+            for (int half = 0; half < 2; ++half, ++hs) {
+                if (!failed.load()) {
+                    const int rc = half_step(g, t, half, hs);
+                    if (rc) {
+                        rcs[g] = rc;
+                        errs[g] = g_err;
+                        failed.store(1);
+                    }
+                }
+                bar.wait();                     // all events of this half-step are recorded
+            }
+            if (chain_dev && (t + 1) % thin == 0) {
+                if (g == 0 && !failed.load()) {
+                    const int rc = store_chain(t, hs);
+                    if (rc) {
+                        rcs[g] = rc;
+                        errs[g] = g_err;
+                        failed.store(1);
+                    }
+                }
+                bar.wait();                     // device 0's event now covers the copy
+            }
+        }
+    };
+    {
+        std::vector<std::thread> pool;
+        pool.reserve(G - 1);
+        for (int g = 1; g < G; ++g) pool.emplace_back(worker, g);
+        worker(0);
+        for (std::thread& th : pool) th.join();
+    }
+    int rc = STN_OK;
+    for (int g = 0; g < G && !rc; ++g)
+        if (rcs[g]) rc = fail(rcs[g], "device %d: %s", m->ctx[g]->device, errs[g].c_str());
     // synchronous on return (also after an error); acceptances summed over the devices
     unsigned long long total = 0;
     for (int g = 0; g < G; ++g) {

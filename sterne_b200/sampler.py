@@ -310,10 +310,16 @@ class FusedEnsembleSampler(object):
             if self.multi.prior is not prior:
                 self.multi.set_prior(prior)
         self.mode = likelihood.mode if mode is None else _lib.MODES[mode]
-        # lanes = 1, splits = 1 is the summation order of the persistent kernel; the launch engine uses the
-        # same plan unless told otherwise, so both engines give the same chain
-        self.plan = _lib.make_plan(1, 1) if plan is None else int(plan)
         self.engine = self.ENGINES[engine]
+        # The persistent kernel sums in the order of plan lanes = 1 | splits = 1; the launch engines (one or
+        # several GPUs) default to the plan of the whole half-ensemble, which keeps all SMs busy.  Give
+        # plan=make_plan(1, 1) to make every engine produce the same chain bit for bit.
+        persistent = self.multi is None and (engine == 'persistent' or (
+            engine == 'auto' and self.mode == _lib.MODE_FAST and ndim <= 64 and self.ctx.problem.evals_per_sample <= 512))
+        if plan is None:
+            self.plan = _lib.make_plan(1, 1) if persistent else self.ctx.auto_plan(nwalkers // 2)
+        else:
+            self.plan = int(plan)
         self.step = 0
         self.chain = None
         self.lnprob = None

@@ -193,7 +193,7 @@ def test_fused_sampler_matches_torch_sampler_statistically():
     # reproducible, and independent of the engine: one persistent cooperative kernel == three launches per half-step
     g = FusedEnsembleSampler(like, prior, nw, seed=11, engine='persistent')
     g.run(p0, 50, thin=5)
-    h = FusedEnsembleSampler(like, prior, nw, seed=11, engine='launches')
+    h = FusedEnsembleSampler(like, prior, nw, seed=11, engine='launches', plan=make_plan(1, 1))
     h.run(p0, 50, thin=5)
     assert torch.equal(g.last[0], h.last[0]) and torch.equal(g.last[1], h.last[1])
     assert torch.equal(g.chain, h.chain) and torch.equal(g.lnprob, h.lnprob)
@@ -217,7 +217,7 @@ def test_fused_sampler_matches_torch_sampler_statistically():
     p3 = case3.truth_vector() + 0.02 * half3 * np.random.default_rng(5).standard_normal((nw3, case3.n_params))
     a3 = FusedEnsembleSampler(like3, prior3, nw3, seed=3, engine='persistent')
     a3.run(p3, 40, thin=1)
-    b3 = FusedEnsembleSampler(like3, prior3, nw3, seed=3, engine='launches')
+    b3 = FusedEnsembleSampler(like3, prior3, nw3, seed=3, engine='launches', plan=make_plan(1, 1))
     b3.run(p3, 40, thin=1)
     assert torch.equal(a3.chain, b3.chain) and torch.equal(a3.lnprob, b3.lnprob)
     assert 0.02 < a3.acceptance_fraction < 0.98

@@ -20,7 +20,7 @@ for W in (1 << 17, 1 << 19):
         s.run(p0, 2, store=False)
         for d in range(G):
             torch.cuda.synchronize(d)
-        n = 10
+        n = 40
         t0 = time.perf_counter()
         s.run(s.last[0], n, store=False)
         for d in range(G):
