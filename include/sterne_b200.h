@@ -218,6 +218,10 @@ int stn_host_alloc(void** ptr, int64_t bytes);
 int stn_host_free(void* ptr);
 int stn_host_register(void* ptr, int64_t bytes);
 int stn_host_unregister(void* ptr);
+/* Tells the host pipeline of this context how many devices copy from this host at the same time
+ * (a launcher with one process per GPU knows, the library cannot): with more than one, chunks
+ * grow twofold instead of fourfold so that each copy still hides under the previous kernel. */
+int stn_host_hint(StnCtx* ctx, int concurrent_devices);
 
 /* ---- several GPUs of one box driven from ONE process ---------------------------
  * The reference is one process with one sampler (simulate.py:191-192) that owns one (N, P)

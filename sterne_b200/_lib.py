@@ -86,6 +86,7 @@ SYMBOLS = [
     ('stn_loglike_timed', _int, [_vp, _vp, _i64, _i64, _int, _int, _int, _vp, _int, c_double_p]),
     ('stn_host_register', _int, [_vp, _i64]),
     ('stn_host_unregister', _int, [_vp]),
+    ('stn_host_hint', _int, [_vp, _int]),
     ('stn_multi_create', _int, [ctypes.POINTER(StnProblem), c_int32_p, _int, ctypes.POINTER(_vp)]),
     ('stn_multi_destroy', _int, [_vp]),
     ('stn_multi_size', _int, [_vp]),

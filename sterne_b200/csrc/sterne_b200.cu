@@ -1274,6 +1274,7 @@ struct StnCtx {
     double* pin_theta[kSlots] = {};
     double* pin_out[kSlots] = {};
     int64_t pin_rows = 0;
+    int host_share = 1;                 // devices DMA-ing from this host at the same time (stn_host_hint)
     cudaStream_t timing_stream = nullptr;
     double* gather_buf = nullptr;       // stn_multi_loglike_dev: this device's slice before the peer copy
     int64_t gather_elems = 0;
@@ -1590,10 +1591,17 @@ int64_t first_chunk_rows(int64_t n) {
     return r < n ? r : n;
 }
 
-int64_t next_chunk_rows(int64_t rows) {
-    const int g = host_schedule().growth > 1 ? host_schedule().growth : 4;    // measured: 4 beats 2 and 8 (profiles/r02_host_schedule.txt)
-    if (rows >= kChunkRowsMax) return kChunkRowsMax;
-    return rows * g < kChunkRowsMax ? rows * g : kChunkRowsMax;
+// Next chunk: fourfold growth when this device has the host's PCIe bandwidth to itself (~50 GB/s: the copy of
+// a 4x larger chunk still hides under the kernel of the current one), twofold when several devices copy at
+// once (stn_multi_*, or stn_host_hint from a multi-process launcher).  Chunks of a wave or more are cut at
+// whole waves of the big kernel so that only the last chunk ends in a partly filled wave.
+int64_t next_chunk_rows(const StnCtx* ctx, int64_t rows) {
+    int g = host_schedule().growth > 1 ? host_schedule().growth : (ctx->host_share > 1 ? 2 : 4);
+    int64_t r = rows >= kChunkRowsMax ? kChunkRowsMax : (rows * g < kChunkRowsMax ? rows * g : kChunkRowsMax);
+    const int bigR = ctx->efac_heavy ? STN_RBIG_EFAC : STN_RBIG;
+    const int64_t wave = (int64_t)ctx->sm_count * minblocks_for(bigR) * threads_for(bigR) * bigR;
+    if (r >= wave) r = (r / wave) * wave;
+    return r;
 }
 
 // One slice of a host batch on this context's device: H2D, kernel(s), D2H, synchronised on return.
@@ -1712,7 +1720,7 @@ int run_host(StnCtx* ctx, const double* theta_host, int64_t n, int64_t ld, int l
                 pend[slot].lo = lo; pend[slot].m = m; pend[slot].live = true;
             }
             lo += m;
-            rows = next_chunk_rows(rows);
+            rows = next_chunk_rows(ctx, rows);
         }
         // the chunks still in flight, oldest first
         for (int j = 0; j < StnCtx::kSlots; ++j) {
@@ -2183,6 +2191,7 @@ int stn_multi_loglike_host(StnMulti* m, const double* theta_host, int64_t n, int
         int64_t lo = 0, hi = 0;
         stn_multi_slice(n, G, g, &lo, &hi);
         StnCtx* c = m->ctx[g];
+        if (c->host_share < G) c->host_share = G;       // G devices copy from this host at once
         if (cudaSetDevice(c->device) != cudaSuccess) {
             rcs[g] = STN_ERR_CUDA;
             errs[g] = "cudaSetDevice failed";
@@ -2462,6 +2471,12 @@ int stn_multi_ensemble_run(StnMulti* m, double* const* x_dev, double* const* lp_
     cudaSetDevice(m->ctx[0]->device);
     if (!rc && n_accept_host) *n_accept_host += (int64_t)total;
     return rc;
+}
+
+int stn_host_hint(StnCtx* ctx, int concurrent_devices) {
+    if (!ctx || concurrent_devices < 1) return fail(STN_ERR_INVALID, "bad argument");
+    ctx->host_share = concurrent_devices;
+    return STN_OK;
 }
 
 int stn_host_register(void* ptr, int64_t bytes) {

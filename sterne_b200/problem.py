@@ -259,6 +259,10 @@ class DeviceContext(object):
         _lib.check(self.lib.stn_model(self.handle, source, theta_ptr, n, ld, layout, mode, radec_ptr,
                                       off_ptr, stream))
 
+    def host_hint(self, concurrent_devices):
+        """How many devices copy from this host at once (one process per GPU: the world size)."""
+        _lib.check(self.lib.stn_host_hint(self.handle, int(concurrent_devices)))
+
     def auto_plan(self, n):
         """Execution plan the library would choose for a batch of n (lanes | splits << 8)."""
         return int(self.lib.stn_auto_plan(self.handle, n))

@@ -136,6 +136,9 @@ class ShardedLikelihood(object):
         self.world = dist.get_world_size(group)
         self._peer = None
         self._flag = None
+        ctx = getattr(likelihood, '_context', None)
+        if ctx is not None and self.world > 1:
+            ctx(None).host_hint(self.world)          # the ranks share this host's PCIe / memory bandwidth
 
     def global_plan(self, n_global):
         ctx = getattr(self.like, '_context', None)
