@@ -102,6 +102,9 @@ namespace {
 constexpr int kThreads = 256;      // threads per CTA of the likelihood kernels
 constexpr int kChunk = STN_CHUNK;  // epochs per shared-memory stage (128 * 96 B = 12 KiB)
 constexpr int kStages = 2;
+constexpr size_t kStageBytes = (size_t)kStages * kChunk * STN_FAST_ROW * sizeof(double);
+#define STN_DYNAMIC_STAGE (STN_CHUNK > 240)          /* 2 x 256 x 96 B + barriers exceeds the 48 KB static limit */
+constexpr size_t kStageSmem = STN_DYNAMIC_STAGE ? kStageBytes + kStages * sizeof(uint64_t) : 0;
 constexpr int kPairUnroll = STN_PAIR_UNROLL;
 constexpr int kEfacUnroll = STN_EFAC_UNROLL;
 constexpr int kFirst = 1, kLast = 2;
@@ -602,8 +605,15 @@ __global__ void __launch_bounds__(TPB, minblocks_tpb(R, TPB))
 stn_loglike_fast_kernel(const ProbDev P, const double* __restrict__ theta, const int64_t N,
                         const int64_t ld, const int layout, double* __restrict__ out,
                         double* __restrict__ partial) {
+    // two stages of the epoch table + their mbarriers: static up to 48 KB, dynamic beyond (256-epoch chunks)
+#if STN_DYNAMIC_STAGE
+    extern __shared__ __align__(128) unsigned char stage_smem[];
+    double (*stage)[kChunk * STN_FAST_ROW] = reinterpret_cast<double (*)[kChunk * STN_FAST_ROW]>(stage_smem);
+    uint64_t* full = reinterpret_cast<uint64_t*>(stage_smem + kStageBytes);
+#else
     __shared__ __align__(128) double stage[kStages][kChunk * STN_FAST_ROW];
     __shared__ __align__(8) uint64_t full[kStages];
+#endif
 
     const int tid = threadIdx.x;
     const int sub = tid % L;
@@ -1395,7 +1405,15 @@ int launch_fast(StnCtx* ctx, const ProbDev& prob, const double* theta, int64_t n
     if (grid > 0x7fffffffLL) return fail(STN_ERR_INVALID, "batch too large for one launch");
     dim3 g((unsigned)grid, (unsigned)splits, 1);
     (void)cudaGetLastError();      // other CUDA users of this process (torch) may have left a stale error
-    stn_loglike_fast_kernel<R, L, TPB><<<g, TPB, 0, st>>>(prob, theta, n, ld, layout, out, partial);
+#if STN_DYNAMIC_STAGE
+    static bool attr_set = false;                    // per instantiation
+    if (!attr_set) {
+        STN_CUDA(cudaFuncSetAttribute(stn_loglike_fast_kernel<R, L, TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)kStageSmem));
+        attr_set = true;
+    }
+#endif
+    stn_loglike_fast_kernel<R, L, TPB><<<g, TPB, kStageSmem, st>>>(prob, theta, n, ld, layout, out, partial);
     STN_CUDA(cudaGetLastError());
     ctx->launches++;
     if (splits > 1) {
