@@ -91,7 +91,13 @@
 #define STN_SAMPLER_CLUSTER 1          /* fused sampler: one thread-block cluster + hardware barrier when <= 16 CTAs */
 #endif
 #ifndef STN_TAIL_SMALL_R
-#define STN_TAIL_SMALL_R 1             /* finish the last, partly filled wave of a big-R launch with the R = 1 kernel */
+#define STN_TAIL_SMALL_R 1             /* finish the last, partly filled wave of a big-R launch with a small-tile kernel */
+#endif
+#ifndef STN_TAIL_R
+#define STN_TAIL_R 2                   /* samples per thread of that tail kernel (64-thread CTAs) */
+#endif
+#ifndef STN_TAIL_MIN_PCT
+#define STN_TAIL_MIN_PCT 10            /* use it when the leftover fills at least this many percent of a wave */
 #endif
 #ifndef STN_RENORM_BITS
 #define STN_RENORM_BITS 900
@@ -1479,21 +1485,22 @@ int launch_loglike(StnCtx* ctx, const double* theta, int64_t n, int64_t ld, int 
     switch (lanes) {
         case 1:
             if (R > 1) {
-                // Wave quantisation: every CTA of the big kernel runs for the same time, so a last wave
-                // that is only partly full costs a whole wave (4.6 waves at 2^19 vectors = 8 % lost).  The
-                // samples beyond the last FULL wave go to the R = 1 kernel in 64-thread CTAs instead: a third
-                // (half) of the samples per thread and many small CTAs that spread evenly over the SMs, so
-                // that tail finishes in well under one big-kernel wave.  R never changes a result bit, so
-                // this is invisible in the output.
+                // Wave quantisation: every CTA of the big kernel runs for the same time, so with FEW waves (the
+                // CTAs are still in lockstep) a last wave that is only partly full costs a whole wave: 4.6 waves
+                // at 2^19 vectors take the time of 5.  The samples beyond the last FULL wave then go to the
+                // R = 2 kernel in 64-thread CTAs: two thirds of the work per thread and many small CTAs that
+                // spread evenly over the SMs (6.40 -> 6.14 ms at 2^19).  After ~10 waves the CTAs have drifted
+                // apart and the partial wave costs little (23.4 ms at 2^21 without, 23.8 with): not used there.
+                // R never changes a result bit, so this is invisible in the output.
                 const int bigR = ctx->efac_heavy ? STN_RBIG_EFAC : STN_RBIG;
                 const int64_t tile = (int64_t)threads_for(bigR) * bigR;
                 const int64_t slots = (int64_t)ctx->sm_count * minblocks_for(bigR);
                 const int64_t tiles = (n + tile - 1) / tile;
                 const int64_t n_main = (tiles / slots) * slots * tile;
-                const int64_t cap1 = (int64_t)ctx->sm_count * minblocks_tpb(1, kTailThreads) * kTailThreads;
-                // measured (profiles/r02_tail_*.json): worth it only when the leftover would fill more than about
-                // half a wave -- 6.39 -> 6.22 ms at 2^19 vectors (0.61 of a wave left) but 23.4 -> 23.7 ms at 2^21 (0.45)
-                const bool worth = 20 * (tiles - (tiles / slots) * slots) >= 11 * slots;
+                constexpr int kTailR = STN_TAIL_R;
+                const int64_t cap1 = (int64_t)ctx->sm_count * minblocks_tpb(kTailR, kTailThreads) * kTailThreads * kTailR;
+                const int64_t left = tiles - (tiles / slots) * slots;                 // tiles of the last, partial wave
+                const bool worth = tiles / slots <= 8 && 100 * left >= STN_TAIL_MIN_PCT * slots && 100 * left <= 85 * slots;
                 if (splits == 1 && n_main > 0 && n_main < n && n - n_main <= cap1 && worth && STN_TAIL_SMALL_R) {
                     int rc = ctx->efac_heavy
                                  ? launch_fast<STN_RBIG_EFAC, 1>(ctx, prob, theta, n_main, ld, layout, out, st, 1, nullptr)
@@ -1502,7 +1509,7 @@ int launch_loglike(StnCtx* ctx, const double* theta, int64_t n, int64_t ld, int 
                     ProbDev tail = prob;
                     for (int k = 0; k < tail.n_extra_out; ++k) tail.extra_out[k] += n_main;
                     const double* th_tail = layout == STN_LAYOUT_AOS ? theta + n_main * ld : theta + n_main;
-                    return launch_fast<1, 1, kTailThreads>(ctx, tail, th_tail, n - n_main, ld, layout, out + n_main, st, 1, nullptr);
+                    return launch_fast<kTailR, 1, kTailThreads>(ctx, tail, th_tail, n - n_main, ld, layout, out + n_main, st, 1, nullptr);
                 }
                 if (ctx->efac_heavy) STN_GO(STN_RBIG_EFAC, 1);
                 STN_GO(STN_RBIG, 1);
