@@ -278,6 +278,9 @@ def run_ours(args, rank, local_rank, world):
     theta = synthetic.device_theta(case, N, seed=1234 + rank, device=dev)
     out = torch.empty(N, dtype=torch.float64, device=dev)
     sharded = ShardedLikelihood(like) if world > 1 else None
+    # the gather fused into the kernel needs the ranks' buffers mapped into each other (CUDA IPC); where that is
+    # impossible every rank falls back to one NCCL all_gather per step, and the line says so
+    fused_gather = bool(sharded.fused_available((1 << LOG2_N) * world)) if world > 1 else False
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -298,12 +301,16 @@ def run_ours(args, rank, local_rank, world):
                 evs[0].record()
             if world == 1:
                 like.log_likelihood_batch(th, out=res, plan=plan)
-            else:
+            elif fused_gather:
                 res = sharded.evaluate_scatter(th, n_global, plan=plan, barrier=False)
+            else:
+                like.log_likelihood_batch(th, out=out[:n_local], plan=plan)
             if evs is not None:
                 evs[1].record()
-            if world > 1:
+            if world > 1 and fused_gather:
                 sharded.barrier()
+            elif world > 1:
+                res = sharded.all_gather(out[:n_local], n_global)
 
         for _ in range(warm):
             one()
@@ -510,9 +517,10 @@ def run_ours(args, rank, local_rank, world):
                            + (' on every rank, each rank\'s slice of the result DMA\'d into ' + assembled if world > 1 else ''),
                     'result_assembled_in': assembled, 'matches_device_path': same, 'pageable': e2e_pageable},
             'gpu_launches': launches,
-            'gather': None if world == 1 else 'fused: the likelihood kernel\'s epilogue stores each log L into every rank\'s '
-                      '(N,) buffer over NVLink (CUDA IPC peer mappings, stn_loglike_scatter); the step ends with a '
-                      'one-element all_reduce as the barrier',
+            'gather': None if world == 1 else (
+                'fused: the likelihood kernel\'s epilogue stores each log L into every rank\'s (N,) buffer over NVLink '
+                '(CUDA IPC peer mappings, stn_loglike_scatter); the step ends with a one-element all_reduce as the barrier'
+                if fused_gather else 'nccl all_gather_into_tensor after the kernel (CUDA IPC unavailable: %s)' % sharded.fused_error),
             'roofline': {
                 'bound': 'fp64', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
                 'frac': achieved_tf / peak_tf,

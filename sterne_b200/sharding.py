@@ -30,6 +30,10 @@ def shard_sizes(n, world_size):
     return [shard_bounds(n, world_size, r)[1] - shard_bounds(n, world_size, r)[0] for r in range(world_size)]
 
 
+class PeerGatherUnavailable(RuntimeError):
+    """The ranks cannot map each other's buffers (raised on every rank together)."""
+
+
 class _DeviceArray(object):
     """Library-owned device memory seen by torch through __cuda_array_interface__."""
 
@@ -59,27 +63,64 @@ class PeerGather(object):
         self.world = dist.get_world_size(group)
         self.device = int(device)
         self.n_max = int(n_max)
-        if self.world > _lib.MAX_OUTS:
-            raise ValueError('PeerGather supports at most %d ranks' % _lib.MAX_OUTS)
-        ptr = ctypes.c_void_p()
-        self.check(self.lib.stn_dev_alloc(self.device, ctypes.byref(ptr), 2 * self.n_max * 8))
-        self.ptr = ptr.value
-        handle = ctypes.create_string_buffer(_lib.IPC_HANDLE_BYTES)
-        self.check(self.lib.stn_ipc_export(self.ptr, handle))
-        handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self.ptr = None
         self.peers = []
-        for r, h in enumerate(handles):
-            if r == self.rank:
-                self.peers.append(self.ptr)
-                continue
-            p = ctypes.c_void_p()
-            buf = ctypes.create_string_buffer(h, _lib.IPC_HANDLE_BYTES)
-            self.check(self.lib.stn_ipc_open(self.device, buf, ctypes.byref(p)))
-            self.peers.append(p.value)
+        if self.world > _lib.MAX_OUTS:
+            raise PeerGatherUnavailable('PeerGather supports at most %d ranks' % _lib.MAX_OUTS)
+        # Every stage is followed by a collective exchange of its outcome, so that a rank where CUDA IPC is not
+        # possible (different nodes, no peer access, a sandbox without IPC) makes ALL ranks give up together
+        # instead of leaving the others inside a collective.
+        handle, err = None, None
+        try:
+            import os
+            if os.environ.get('STERNE_B200_NO_IPC'):              # lets the NCCL fallback be exercised where IPC works
+                raise RuntimeError('disabled by STERNE_B200_NO_IPC')
+            ptr = ctypes.c_void_p()
+            self.check(self.lib.stn_dev_alloc(self.device, ctypes.byref(ptr), 2 * self.n_max * 8))
+            self.ptr = ptr.value
+            buf = ctypes.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+            self.check(self.lib.stn_ipc_export(self.ptr, buf))
+            handle = bytes(buf.raw)
+        except Exception as e:                      # noqa: BLE001 - reported collectively below
+            err = str(e)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle, group=group)
+        if any(h is None for h in handles):
+            self._release()
+            raise PeerGatherUnavailable('CUDA IPC export failed on rank(s) %s%s' % (
+                [r for r, h in enumerate(handles) if h is None], ': ' + err if err else ''))
+        opened = [None] * self.world
+        err = None
+        try:
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    opened[r] = self.ptr
+                    continue
+                p = ctypes.c_void_p()
+                hb = ctypes.create_string_buffer(h, _lib.IPC_HANDLE_BYTES)
+                self.check(self.lib.stn_ipc_open(self.device, hb, ctypes.byref(p)))
+                opened[r] = p.value
+        except Exception as e:                      # noqa: BLE001
+            err = str(e)
+        self.peers = opened
+        oks = [None] * self.world
+        dist.all_gather_object(oks, err is None, group=group)
+        if not all(oks):
+            self._release()
+            raise PeerGatherUnavailable('CUDA IPC open failed on rank(s) %s%s' % (
+                [r for r, ok in enumerate(oks) if not ok], ': ' + err if err else ''))
         self.local = torch.as_tensor(_DeviceArray(self.ptr, 2 * self.n_max), device=torch.device('cuda', self.device))
         self.parity = 0
         dist.barrier(group=group)
+
+    def _release(self):
+        for r, p in enumerate(self.peers):
+            if p and r != self.rank:
+                self.lib.stn_ipc_close(self.device, p)
+        self.peers = []
+        if self.ptr:
+            self.lib.stn_dev_free(self.device, self.ptr)
+            self.ptr = None
 
     def outs(self, lo, roots=None):
         """Pointers to element `lo` of the current buffers of `roots` (default: every rank), own buffer first."""
@@ -101,12 +142,8 @@ class PeerGather(object):
                 dist.barrier(group=self.group)            # nobody may still be writing into a buffer that goes away
             except Exception:
                 pass
-            for r, p in enumerate(self.peers):
-                if r != self.rank:
-                    self.lib.stn_ipc_close(self.device, p)
             self.local = None
-            self.lib.stn_dev_free(self.device, self.ptr)
-            self.ptr = None
+            self._release()
 
     def __del__(self):
         try:
@@ -136,6 +173,8 @@ class ShardedLikelihood(object):
         self.world = dist.get_world_size(group)
         self._peer = None
         self._flag = None
+        self._fused_ok = None
+        self.fused_error = None
         ctx = getattr(likelihood, '_context', None)
         if ctx is not None and self.world > 1:
             ctx(None).host_hint(self.world)          # the ranks share this host's PCIe / memory bandwidth
@@ -154,12 +193,25 @@ class ShardedLikelihood(object):
 
     # ------------------------------------------------------------------ fused compute + gather
     def peer_gather(self, n_global):
-        """The PeerGather of this object, (re)built when a larger batch comes along (collective)."""
+        """The PeerGather of this object, (re)built when a larger batch comes along (collective).
+        Raises PeerGatherUnavailable on every rank when the buffers cannot be mapped."""
         if self._peer is None or self._peer.n_max < n_global:
             if self._peer is not None:
                 self._peer.close()
+                self._peer = None
             self._peer = PeerGather(n_global, self.like.device, self.group)
         return self._peer
+
+    def fused_available(self, n_global):
+        """True when the kernel-stores-to-peers gather can be used for batches of n_global (collective; tried once)."""
+        if self._fused_ok is None or (self._fused_ok and (self._peer is None or self._peer.n_max < n_global)):
+            try:
+                self.peer_gather(n_global)
+                self._fused_ok = True
+            except PeerGatherUnavailable as e:
+                self._fused_ok = False
+                self.fused_error = str(e)
+        return self._fused_ok
 
     def evaluate_scatter(self, theta_local, n_global, keys=None, mode=None, plan=None, roots=None, barrier=True):
         """Fused path: this rank's slice (a CUDA tensor whose rows are [lo, hi) of the global batch) is
@@ -227,7 +279,7 @@ class ShardedLikelihood(object):
         lo, hi = self.local_slice(n)
         is_cuda = hasattr(theta_global, 'is_cuda') and theta_global.is_cuda
         if fused is None:
-            fused = is_cuda and self.world <= 8 and hasattr(self.like, '_context')
+            fused = is_cuda and self.world <= 8 and hasattr(self.like, '_context') and self.fused_available(n)
         if fused:
             import torch
             return self.evaluate_scatter(theta_global[lo:hi], n, **kw).clone()

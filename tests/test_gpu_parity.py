@@ -644,7 +644,7 @@ def test_scatter_launch_writes_every_output_buffer():
     like = case.likelihood()
     ctx = like._context(None)
     dev = torch.device('cuda', 0)
-    n = 148 * 4 * 192 + 7777                       # one full wave of the R = 3 kernel + a tail for the R = 1 kernel
+    n = 148 * 4 * 192 + 30000                      # one full wave of the R = 3 kernel + a tail for the small-tile kernel
     theta = synthetic.device_theta(case, n, seed=3, device=dev)
     st = torch.cuda.current_stream(dev).cuda_stream
     for mode, plan in ((_lib.MODE_FAST, make_plan(1)), (_lib.MODE_FAST, make_plan(1, 4)), (_lib.MODE_STRICT, 0)):
@@ -662,8 +662,9 @@ def test_scatter_launch_writes_every_output_buffer():
 
 
 def test_small_r_tail_is_invisible_in_the_bits():
-    """A batch whose last big-kernel wave is partly filled is finished by the R = 1 kernel; samples per
-    thread never change a bit: the same vectors evaluated alone (R = 1 throughout) give the same values."""
+    """A batch of few waves whose last big-kernel wave is partly filled is finished by the small-tile (R = 2,
+    64-thread) kernel; samples per thread never change a bit: the same vectors evaluated alone (R = 1
+    throughout) give the same values."""
     import torch
     case = synthetic.config5('C', n_epochs=128)
     like = case.likelihood()
