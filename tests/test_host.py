@@ -223,3 +223,47 @@ def test_unit_factors_are_injectable(monkeypatch):
     bad.mas = types.SimpleNamespace(name='mas', to=lambda t: 1.0, __truediv__=None)
     assert not constants.use_astropy(bad, c)
     assert constants.MAS2RAD == saved['MAS2RAD']
+
+
+def test_routing_properties_on_random_shares():
+    """hypothesis: for ANY shares matrix (1..13 sources, values -1..4 per row) the names equal the oracle's
+    restatement of priors.get_parameters_from_shares, every name parses back to its sources and root,
+    and the integer column table routes exactly the value the reference's dict filter + sorted positional
+    pick would hand to position() -- including the -999 fill for absent roots and two-digit source indices."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.integers(min_value=1, max_value=13).flatmap(
+        lambda S: st.lists(st.lists(st.integers(min_value=-1, max_value=4), min_size=S, max_size=S),
+                           min_size=9, max_size=9)))
+    def check(shares):
+        S = len(shares[0])
+        names = list(sb.get_parameters_from_shares(shares))
+        assert names == list(O.get_parameters_from_shares(shares))
+        assert len(set(names)) == len(names)
+        for root_i, row in enumerate(shares):                      # every present (source, root) is named exactly once
+            for s, v in enumerate(row):
+                owners = [n for n in names if sh.parameter_name_to_pmparin_indice(n) ==
+                          (sh.parameter_name_to_pmparin_indice(n)[0], sb.ROOTS[root_i])
+                          and s in sh.parameter_name_to_pmparin_indice(n)[0]]
+                assert len(owners) == (1 if v >= 0 else 0)
+        if not names:
+            return
+        idx = sh.column_table(names, S)
+        values = {k: 10.0 + i for i, k in enumerate(names)}
+        for s in range(S):
+            FP = O.filter_dictionary_of_parameter_with_index(values, s)
+            Ps = sorted(FP.keys())
+            assert len(Ps) == 9
+            for r in range(9):
+                got = -999 if idx[s, r] < 0 else values[names[idx[s, r]]]
+                assert got == FP[Ps[r]], (shares, s, r)
+            assert sh.filter_dictionary_of_parameter_with_index(values, s) == FP
+        # sources that share a value share the column
+        for r, row in enumerate(shares):
+            for a in range(S):
+                for b in range(S):
+                    if row[a] >= 0 and row[a] == row[b]:
+                        assert idx[a, r] == idx[b, r] >= 0
+
+    check()
