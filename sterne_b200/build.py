@@ -26,7 +26,9 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [SRC, os.path.join(ROOT, 'include', 'sterne_b200.h'), os.path.abspath(__file__)]
+    csrc = os.path.dirname(SRC)
+    deps = [os.path.join(csrc, f) for f in os.listdir(csrc)] + [os.path.join(ROOT, 'include', 'sterne_b200.h'),
+                                                                os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
