@@ -83,6 +83,7 @@ int64_t first_chunk_rows(int64_t n) {
 // once (stn_multi_*, or stn_host_hint from a multi-process launcher).  Chunks of a wave or more are cut at
 // whole waves of the big kernel so that only the last chunk ends in a partly filled wave.
 int64_t next_chunk_rows(const StnCtx* ctx, int64_t rows) {
+    // (twofold growth for pageable, staged input was tried as well: 55.1 ms instead of 52.6 at 2^22 rows)
     int g = host_schedule().growth > 1 ? host_schedule().growth : (ctx->host_share > 1 ? 2 : 4);
     int64_t r = rows >= kChunkRowsMax ? kChunkRowsMax : (rows * g < kChunkRowsMax ? rows * g : kChunkRowsMax);
     const int bigR = ctx->efac_heavy ? STN_RBIG_EFAC : STN_RBIG;
