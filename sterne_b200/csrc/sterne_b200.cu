@@ -94,6 +94,9 @@
 #ifndef STN_SAMPLER_CLUSTER
 #define STN_SAMPLER_CLUSTER 1          /* fused sampler: one thread-block cluster + hardware barrier when <= 16 CTAs */
 #endif
+#ifndef STN_BIGR_MIN_TENTH_WAVES
+#define STN_BIGR_MIN_TENTH_WAVES 8     /* the big-R kernel is used once its CTAs fill this many tenths of a wave */
+#endif
 #ifndef STN_TAIL_SMALL_R
 #define STN_TAIL_SMALL_R 1             /* finish the last, partly filled wave of a big-R launch with a small-tile kernel */
 #endif

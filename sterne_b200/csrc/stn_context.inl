@@ -119,14 +119,16 @@ inline int make_plan(int lanes, int splits) { return lanes | (splits << 8); }
 
 int big_R(const StnCtx* ctx) { return ctx->efac_heavy ? STN_RBIG_EFAC : STN_RBIG; }
 
-// R used for a batch of n with `splits` CTAs per tile: the big R once its tiles fill the SMs
+// R used for a batch of n with `splits` CTAs per tile: the big R once its tiles fill most of a wave
 int choose_R(const StnCtx* ctx, int64_t n, int lanes, int splits) {
     if (lanes != 1) return 1;
     const int R = big_R(ctx);
     const int64_t slots = (int64_t)ctx->sm_count * minblocks_for(R);
     const int64_t tile = (int64_t)threads_for(R) * R;
     const int64_t tiles = (n + tile - 1) / tile;
-    return tiles * splits >= 2 * slots ? R : 1;
+    // measured, variant C, plan lanes=1|splits=1: at 0.58 of a wave R = 1 wins (1.05 vs 1.37 ms), from 0.82 of a
+    // wave on the big kernel does (1.36 vs 1.54 ms; 1.15 waves: 1.96 vs 2.03; 1.75 waves: 2.81 vs 3.01)
+    return 10 * tiles * splits >= STN_BIGR_MIN_TENTH_WAVES * slots ? R : 1;
 }
 
 int pick_plan(const StnCtx* ctx, int64_t n) {

@@ -7,14 +7,14 @@ import torch
 from sterne_b200 import synthetic, fp64_peak
 
 ap = argparse.ArgumentParser()
-ap.add_argument('--log2n', type=int, default=22)
+ap.add_argument('--log2n', type=float, default=22)
 ap.add_argument('--steps', type=int, default=5)
 ap.add_argument('--variants', default='ABC')
 ap.add_argument('--plan', type=int, default=0)
 ap.add_argument('--check', action='store_true')
 a = ap.parse_args()
 dev = torch.device('cuda', 0)
-N = 1 << a.log2n
+N = int(round(2 ** a.log2n))
 flops = {'A': 30.0, 'B': 42.0, 'C': 43.5}
 res = {'lib': os.environ.get('STERNE_B200_LIB', 'default'), 'log2n': a.log2n}
 for v in a.variants:

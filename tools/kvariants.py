@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ap = argparse.ArgumentParser()
 ap.add_argument('--variants', default='C')
 ap.add_argument('--steps', type=int, default=5)
-ap.add_argument('--log2n', type=int, default=22)
+ap.add_argument('--log2n', type=float, default=22)
 ap.add_argument('--out', default=os.path.join(ROOT, 'gpurun_out', 'kvariants.json'))
 ap.add_argument('--only', default='')
 ap.add_argument('--plan', type=int, default=0)
