@@ -267,3 +267,26 @@ def test_routing_properties_on_random_shares():
                         assert idx[a, r] == idx[b, r] >= 0
 
     check()
+
+
+def test_c_slices_equal_python_shard_bounds():
+    """stn_multi_slice (one process, several GPUs) and sharding.shard_bounds (one process per GPU) cut a batch
+    the same way -- the C function is pure arithmetic and runs without a GPU."""
+    import ctypes
+    from sterne_b200.sharding import shard_bounds
+    lib = _lib.load()
+    lo, hi = ctypes.c_int64(), ctypes.c_int64()
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        n = int(rng.integers(0, 1 << 23))
+        g = int(rng.integers(1, 9))
+        prev = 0
+        for part in range(g):
+            assert lib.stn_multi_slice(n, g, part, ctypes.byref(lo), ctypes.byref(hi)) == 0
+            assert (lo.value, hi.value) == shard_bounds(n, g, part)
+            assert lo.value == prev
+            prev = hi.value
+        assert prev == n
+    assert lib.stn_multi_slice(10, 0, 0, ctypes.byref(lo), ctypes.byref(hi)) != 0
+    assert lib.stn_multi_slice(10, 2, 2, ctypes.byref(lo), ctypes.byref(hi)) != 0
+    assert b'slice' in lib.stn_last_error()
