@@ -94,6 +94,9 @@
 #ifndef STN_SAMPLER_CLUSTER
 #define STN_SAMPLER_CLUSTER 1          /* fused sampler: one thread-block cluster + hardware barrier when <= 16 CTAs */
 #endif
+#ifndef STN_ROW_PREFETCH
+#define STN_ROW_PREFETCH 0             /* EFAC loop: fetch the next epoch's row while the current one is used */
+#endif
 #ifndef STN_BIGR_MIN_TENTH_WAVES
 #define STN_BIGR_MIN_TENTH_WAVES 8     /* the big-R kernel is used once its CTAs fill this many tenths of a wave */
 #endif

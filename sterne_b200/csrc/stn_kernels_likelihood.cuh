@@ -241,40 +241,49 @@ struct Acc {
 };
 
 // Residuals of one epoch of one sample, and for EFAC sources the two variances.
+// One staged epoch row in registers (the pairs of the fast table that the variant needs).
+struct Row {
+    double2 tx, yz, ob, aa, bb, bc;
+};
+
 template <bool EF, bool BIN>
-__device__ __forceinline__ void epoch_residuals(const double* __restrict__ rows, int e, const Coef& cf,
-                                                double& res_ra, double& res_dec, double& v_ra, double& v_dec,
-                                                double2& aa) {
+__device__ __forceinline__ Row load_row(const double* __restrict__ rows, int e) {
     STN_ASSERT(e >= 0 && e < kChunk);
     const double2* row = reinterpret_cast<const double2*>(rows + e * STN_FAST_ROW);
-    const double2 tx = row[0];
-    const double2 yz = row[1];
-    const double2 ob = row[2];
-    aa = row[3];
-    double2 bc = make_double2(0.0, 0.0);
-    if (BIN) bc = row[5];
+    Row r;
+    r.tx = row[0];
+    r.yz = row[1];
+    r.ob = row[2];
+    r.aa = row[3];
+    r.bb = EF ? row[4] : make_double2(0.0, 0.0);
+    r.bc = BIN ? row[5] : make_double2(0.0, 0.0);
+    return r;
+}
+
+// Residuals of one epoch of one sample, and for EFAC sources the two variances.
+template <bool EF, bool BIN>
+__device__ __forceinline__ void epoch_residuals(const Row& w, const Coef& cf, double& res_ra, double& res_dec,
+                                                double& v_ra, double& v_dec) {
     double ora, odec;
-    fast_offsets<BIN>(cf, tx, yz, bc, ora, odec);
+    fast_offsets<BIN>(cf, w.tx, w.yz, w.bc, ora, odec);
     // model = ref + offset (rad); residual = obs - model   (positions.py:119-120,
     // simulate.py:368).  This order is kept: the subtraction cancels ~9 digits.
-    res_ra = ob.x - (cf.ra + ora);
-    res_dec = ob.y - (cf.dec + odec);
+    res_ra = w.ob.x - (cf.ra + ora);
+    res_dec = w.ob.y - (cf.dec + odec);
     if (EF) {
-        const double2 bb = row[4];
-        v_ra = fma(cf.g_ra, bb.x, aa.x);                  // simulate.py:317 (table pre-scaled by 2^k)
-        v_dec = fma(cf.g_dec, bb.y, aa.y);
+        v_ra = fma(cf.g_ra, w.bb.x, w.aa.x);              // simulate.py:317 (table pre-scaled by 2^k)
+        v_dec = fma(cf.g_dec, w.bb.y, w.aa.y);
     }
 }
 
 // One epoch of one sample.
 template <bool EF, bool BIN>
-__device__ __forceinline__ void epoch_term(const double* __restrict__ rows, int e, const Coef& cf, Acc& acc) {
+__device__ __forceinline__ void epoch_term(const Row& w, const Coef& cf, Acc& acc) {
     double res_ra, res_dec, v_ra = 1.0, v_dec = 1.0;
-    double2 aa;
-    epoch_residuals<EF, BIN>(rows, e, cf, res_ra, res_dec, v_ra, v_dec, aa);
+    epoch_residuals<EF, BIN>(w, cf, res_ra, res_dec, v_ra, v_dec);
     if (!EF) {
-        const double z_ra = res_ra * aa.x;
-        const double z_dec = res_dec * aa.y;
+        const double z_ra = res_ra * w.aa.x;
+        const double z_dec = res_dec * w.aa.y;
         acc.chi_ra = fma(z_ra, z_ra, acc.chi_ra);
         acc.chi_dec = fma(z_dec, z_dec, acc.chi_dec);
     } else {
@@ -303,13 +312,26 @@ __device__ __forceinline__ void epoch_loop(const double* __restrict__ rows, int 
                                            const Coef (&cf)[R], Acc (&acc)[R], int mask) {
     int e = sub;
     if constexpr (EF) {
+#if STN_ROW_PREFETCH
+        // the row of the NEXT epoch is fetched while the current one is being used, so no warp starts an
+        // iteration by waiting for shared memory (rows past n_epochs are stale but inside the stage, and unused)
+        Row cur = load_row<true, BIN>(rows, e < kChunk ? e : kChunk - 1);
+#endif
         while (e < n_epochs) {
             const int span = (mask + 1) * L;
             const int stop = (n_epochs - e > span) ? e + span : n_epochs;
 #pragma unroll kEfacUnroll
             for (; e < stop; e += L) {
+#if STN_ROW_PREFETCH
+                const Row nxt = load_row<true, BIN>(rows, e + L < kChunk ? e + L : kChunk - 1);
 #pragma unroll
-                for (int r = 0; r < R; ++r) epoch_term<true, BIN>(rows, e, cf[r], acc[r]);
+                for (int r = 0; r < R; ++r) epoch_term<true, BIN>(cur, cf[r], acc[r]);
+                cur = nxt;
+#else
+                const Row w = load_row<true, BIN>(rows, e);
+#pragma unroll
+                for (int r = 0; r < R; ++r) epoch_term<true, BIN>(w, cf[r], acc[r]);
+#endif
             }
 #pragma unroll
             for (int r = 0; r < R; ++r) renorm(acc[r]);
@@ -317,15 +339,18 @@ __device__ __forceinline__ void epoch_loop(const double* __restrict__ rows, int 
     } else {
 #pragma unroll kPairUnroll
         for (; e + L < n_epochs; e += 2 * L) {
+            const Row w0 = load_row<false, BIN>(rows, e);
+            const Row w1 = load_row<false, BIN>(rows, e + L);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                epoch_term<false, BIN>(rows, e, cf[r], acc[r]);
-                epoch_term<false, BIN>(rows, e + L, cf[r], acc[r]);
+                epoch_term<false, BIN>(w0, cf[r], acc[r]);
+                epoch_term<false, BIN>(w1, cf[r], acc[r]);
             }
         }
         if (e < n_epochs) {
+            const Row w = load_row<false, BIN>(rows, e);
 #pragma unroll
-            for (int r = 0; r < R; ++r) epoch_term<false, BIN>(rows, e, cf[r], acc[r]);
+            for (int r = 0; r < R; ++r) epoch_term<false, BIN>(w, cf[r], acc[r]);
         }
     }
 }
