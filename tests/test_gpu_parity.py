@@ -702,3 +702,35 @@ def test_injected_unit_factor_reaches_the_kernels(monkeypatch):
         monkeypatch.setattr(O, 'MAS2RAD', other)
         want, _ = O.batch_model(case.refepoch, case.LoD_VLBI[0], case.earth_xyz[0], case.LoD_timing[0], idx[0], theta)
         assert np.abs(got - want).max() <= 2 * np.spacing(6.3)     # ... exactly as the oracle's move with it
+
+
+@pytest.mark.parametrize('decades', [4, 10, 16])
+def test_heterogeneous_variances_and_wild_efac(decades):
+    """The EFAC running fraction (T, Q) under adversarial tables: errors spread over `decades` orders of
+    magnitude WITHIN one source (so products of a few variances leave any fixed window), random
+    random/systematic splits, and efac from 1e-8 to 1e5 in the same batch (the renormalisation cadence
+    is chosen per warp from the worst lane)."""
+    case = _multi_case(9, (300, 140), efac=True, binaries=(1,))
+    rng = np.random.default_rng(decades)
+    for v in case.LoD_VLBI:
+        n = len(v['errs'])
+        errs = 10.0 ** rng.uniform(-13.0, -13.0 + decades, n)
+        frac = rng.uniform(0.05, 0.95, n)
+        v['errs'] = errs
+        v['errs_random'] = errs * frac
+        v['errs_sys'] = np.sqrt(errs ** 2 - v['errs_random'] ** 2)
+    theta = case.sample_theta(512, seed=4)
+    col = case.names.index([k for k in case.names if k.startswith('efac')][0])
+    theta[:, col] = 10.0 ** rng.uniform(-8.0, 5.0, theta.shape[0])
+    theta[::7, col] = 1.0
+    want = _oracle_batch(case, theta)
+    assert np.isfinite(want).all()
+    scale = max(logl_scale(case.LoD_VLBI), 1.0)
+    like = case.likelihood()
+    for plan in (0, make_plan(1), make_plan(4), make_plan(1, 3)):
+        got = like.log_likelihood_batch(theta, plan=plan)
+        assert np.isfinite(got).all()
+        assert logl_err(got, want, scale).max() < LOGL_RTOL, (decades, plan, logl_err(got, want, scale).max())
+    strict = like.log_likelihood_batch(theta, mode='strict')
+    assert logl_err(strict, want, scale).max() < LOGL_RTOL
+    like.close()
