@@ -524,8 +524,8 @@ __device__ __forceinline__ void store_result(const ProbDev& P, double* __restric
 __host__ __device__ constexpr int threads_for(int R) { return R > 2 ? STN_THREADS_R3 : (R == 2 ? STN_THREADS_R2 : kThreads); }
 __host__ __device__ constexpr int minblocks_for(int R) { return R > 2 ? STN_MINBLOCKS_R3 : (R == 2 ? STN_MINBLOCKS_R2 : 2); }
 
-// TPB: threads per CTA (default: the shape chosen for R); TPB = kTailThreads is the small-CTA form of the
-// R = 1 kernel that finishes the last, partly filled wave of a big launch
+// TPB: threads per CTA (default: the shape chosen for R); TPB = kTailThreads is the small-CTA form (with
+// R = STN_TAIL_R) that finishes the last, partly filled wave of a big launch
 constexpr int kTailThreads = 64;
 __host__ __device__ constexpr int minblocks_tpb(int R, int tpb) { return tpb == threads_for(R) ? minblocks_for(R) : 8; }
 

@@ -389,10 +389,8 @@ def test_edge_shapes_match_oracle(epoch_counts, binaries, a1dot):
 
 @pytest.mark.parametrize('scale', [1e-45, 1e-5, 1e6])
 def test_extreme_variance_tables(scale):
-    """Errors scaled far away from the usual 1e-10 rad.  1e-45: a product of a few variances would
-    underflow, the library must fall back to per-variance reciprocals and exponent extraction;
-    1e-5 (variances ~1e-29): still on the grouped path, where eight variances are multiplied
-    (1e-230) before one extraction; 1e6: large errors."""
+    """Errors scaled far away from the usual 1e-10 rad: 1e-45 (variances ~1e-110: any product of a few of
+    them would underflow without the per-source power-of-two pre-scaling of the table), 1e-5, 1e6."""
     case = _multi_case(5, (40,), efac=True)
     v = case.LoD_VLBI[0]
     for k in ('errs', 'errs_random', 'errs_sys'):
@@ -716,6 +714,8 @@ def test_heterogeneous_variances_and_wild_efac(decades):
         n = len(v['errs'])
         errs = 10.0 ** rng.uniform(-13.0, -13.0 + decades, n)
         frac = rng.uniform(0.05, 0.95, n)
+        frac[rng.random(n) < 0.05] = 0.0               # no random error at all: nothing bounds those variances from below
+        frac[rng.random(n) < 0.05] = 1.0               # no systematic error: the variance does not depend on efac
         v['errs'] = errs
         v['errs_random'] = errs * frac
         v['errs_sys'] = np.sqrt(errs ** 2 - v['errs_random'] ** 2)
