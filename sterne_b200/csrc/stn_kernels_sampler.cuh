@@ -288,54 +288,94 @@ stn_ensemble_kernel(const ProbDev P0, double* x, double* lp, const int64_t W, co
     const int64_t Hpad = (H + 31) / 32 * 32;             // whole warps walk the loop together
     unsigned long long accepted = 0;
     double y[STN_SAMPLER_MAX_P];
-    for (int64_t t = 0; t < n_steps; ++t) {
-        const uint64_t step = step0 + (uint64_t)t;
-        for (int half = 0; half < 2; ++half) {
-            for (int64_t kk = gtid; kk < Hpad; kk += nthreads) {
-                const bool valid = kk < H;
-                const int64_t k = valid ? kk : H - 1;
-                // this walker's row and log-posterior do not depend on the random numbers: their L2 round trip
-                // (the barrier invalidated L1) overlaps the Philox rounds
-                const int64_t i = half ? H + k : k;
-                const double* xi = x + i * ld;
-                for (int p = 0; p < np; ++p) y[p] = __ldcg(xi + p);
-                const double lp_i = __ldcg(lp + i);
-                uint32_t r[4];
-                philox4x32_10((uint32_t)k, (uint32_t)(k >> 32), (uint32_t)step,
-                              (uint32_t)(step >> 32) ^ (half ? 0x80000000u : 0u), (uint32_t)seed, (uint32_t)(seed >> 32), r);
-                const double u = u01(r[0], r[1]);
-                const double tt = (a - 1.0) * u + 1.0;
-                const double z = tt * tt / a;
-                const int64_t j = (int64_t)(u01(r[2], r[3]) * (double)H);
-                const double* xj = x + (half ? j : H + j) * ld;
-                uint32_t r2[4];
-                philox4x32_10((uint32_t)k, (uint32_t)(k >> 32), (uint32_t)step,
-                              (uint32_t)(step >> 32) ^ (half ? 0xC0000000u : 0x40000000u), (uint32_t)seed,
-                              (uint32_t)(seed >> 32), r2);                        // accept draw, while the partner row arrives
-                for (int p = 0; p < np; ++p) {
-                    const double vj = __ldcg(xj + p);
-                    y[p] = fma(z, y[p] - vj, vj);
-                }
-                const double lpy = logpost_one<true>(P, y, np);
-                const double lnq = (double)(np - 1) * log(z) + lpy - lp_i;
-                const bool acc = valid && (lpy > -CUDART_INF) && (lpy == lpy) && (log(u01(r2[0], r2[1])) < lnq);
-                if (acc) {
-                    for (int p = 0; p < np; ++p) x[i * ld + p] = y[p];
-                    lp[i] = lpy;
-                    ++accepted;
-                }
-            }
-            sampler_barrier(cluster_mode != 0);        // the other half reads these walkers next
+
+    // Everything of a proposal that does not depend on the half-step that is still being written: the random
+    // numbers, this walker's own row (it belongs to the half that is NOT being updated) and its log-posterior.
+    struct Draw {
+        int64_t i, jrow;
+        double z, logz, lnu, lp_i;
+        bool valid;
+    };
+    auto prepare = [&](int64_t kk, uint64_t step, int half, Draw& d) {
+        d.valid = kk < H;
+        const int64_t k = d.valid ? kk : H - 1;
+        d.i = half ? H + k : k;
+        const double* xi = x + d.i * ld;
+        for (int p = 0; p < np; ++p) y[p] = __ldcg(xi + p);
+        d.lp_i = __ldcg(lp + d.i);
+        uint32_t r[4];
+        philox4x32_10((uint32_t)k, (uint32_t)(k >> 32), (uint32_t)step, (uint32_t)(step >> 32) ^ (half ? 0x80000000u : 0u),
+                      (uint32_t)seed, (uint32_t)(seed >> 32), r);
+        const double u = u01(r[0], r[1]);
+        const double tt = (a - 1.0) * u + 1.0;
+        d.z = tt * tt / a;
+        d.logz = log(d.z);
+        d.jrow = (half ? 0 : H) + (int64_t)(u01(r[2], r[3]) * (double)H);
+        philox4x32_10((uint32_t)k, (uint32_t)(k >> 32), (uint32_t)step,
+                      (uint32_t)(step >> 32) ^ (half ? 0xC0000000u : 0x40000000u), (uint32_t)seed, (uint32_t)(seed >> 32), r);
+        d.lnu = log(u01(r[0], r[1]));
+    };
+    // The part that needs the partner's CURRENT position: proposal, log-posterior, accept / reject.
+    auto finish = [&](const Draw& d) {
+        const double* xj = x + d.jrow * ld;
+        for (int p = 0; p < np; ++p) {
+            const double vj = __ldcg(xj + p);
+            y[p] = fma(d.z, y[p] - vj, vj);
         }
-        if (chain != nullptr && (t + 1) % thin == 0) {
-            const int64_t slot = (t + 1) / thin - 1;
-            for (int64_t e = gtid; e < W * np; e += nthreads) {
-                const int64_t w = e / np;
-                chain[slot * W * np + e] = __ldcg(x + w * ld + (e - w * np));
+        const double lpy = logpost_one<true>(P, y, np);
+        const double lnq = (double)(np - 1) * d.logz + lpy - d.lp_i;
+        if (d.valid && (lpy > -CUDART_INF) && (lpy == lpy) && (d.lnu < lnq)) {
+            for (int p = 0; p < np; ++p) x[d.i * ld + p] = y[p];
+            lp[d.i] = lpy;
+            ++accepted;
+        }
+    };
+    auto store_chain = [&](int64_t t) {
+        const int64_t slot = (t + 1) / thin - 1;
+        for (int64_t e = gtid; e < W * np; e += nthreads) {
+            const int64_t w = e / np;
+            chain[slot * W * np + e] = __ldcg(x + w * ld + (e - w * np));
+        }
+        if (lnprob != nullptr)
+            for (int64_t w = gtid; w < W; w += nthreads) lnprob[slot * W + w] = __ldcg(lp + w);
+    };
+
+    if (cluster_mode != 0 && Hpad <= nthreads) {
+        // One proposal per thread and a hardware cluster barrier: the barrier is SPLIT.  After a thread has
+        // stored its accepted walker it arrives, prepares its next proposal (two Philox draws, its own row from
+        // L2, two logarithms) while the other CTAs finish, and only then waits -- the barrier's latency and the
+        // L2 round trip hide behind work that is needed anyway.
+        const bool active = gtid < Hpad;
+        Draw d;
+        if (active) prepare(gtid, step0, 0, d);
+        for (int64_t t = 0; t < n_steps; ++t) {
+            for (int half = 0; half < 2; ++half) {
+                if (active) finish(d);
+                asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+                const bool more = !(t == n_steps - 1 && half == 1);
+                if (active && more) prepare(gtid, step0 + (uint64_t)(half ? t + 1 : t), half ^ 1, d);
+                asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
             }
-            if (lnprob != nullptr)
-                for (int64_t w = gtid; w < W; w += nthreads) lnprob[slot * W + w] = __ldcg(lp + w);
-            sampler_barrier(cluster_mode != 0);        // half-step 0 of the next step overwrites rows that are being copied
+            if (chain != nullptr && (t + 1) % thin == 0) {
+                store_chain(t);
+                sampler_barrier(true);              // half-step 0 of the next step overwrites rows that are being copied
+            }
+        }
+    } else {
+        for (int64_t t = 0; t < n_steps; ++t) {
+            const uint64_t step = step0 + (uint64_t)t;
+            for (int half = 0; half < 2; ++half) {
+                for (int64_t kk = gtid; kk < Hpad; kk += nthreads) {
+                    Draw d;
+                    prepare(kk, step, half, d);
+                    finish(d);
+                }
+                sampler_barrier(cluster_mode != 0);        // the other half reads these walkers next
+            }
+            if (chain != nullptr && (t + 1) % thin == 0) {
+                store_chain(t);
+                sampler_barrier(cluster_mode != 0);        // half-step 0 of the next step overwrites rows that are being copied
+            }
         }
     }
     for (int o = 16; o > 0; o >>= 1) accepted += __shfl_xor_sync(0xffffffffu, accepted, o);
