@@ -54,7 +54,7 @@ enum StnLayout {
 };
 
 enum StnMode {
-    STN_MODE_FAST = 0,      /* hoisted per-(sample,source) coefficients, FMA, reciprocals */
+    STN_MODE_FAST = 0,      /* hoisted per-(sample,source) coefficients, FMA, chi-square as a running fraction */
     STN_MODE_STRICT = 1     /* the reference's operation order, one rounding per operation
                                (positions.py:108-120,308-309; simulate.py:317-320,368-371) */
 };
