@@ -102,7 +102,10 @@ int run_host(StnCtx* ctx, const double* theta_host, int64_t n, int64_t ld, int l
     // Small batches (a sampler evaluating one point, or a few walkers) are latency-bound: skip both
     // cudaMemcpy calls by letting the kernel read the parameters from, and write log L to, pinned
     // mapped host memory.  One launch + one stream synchronise.
-    constexpr int64_t kSmallBytes = 64 * 1024, kSmallRows = 2048;
+    // (limits tunable through the environment; measured with tools/latency_host.py: raising them to 8192 rows / 2 MB
+    // does not help 6-parameter batches and doubles the latency of 16-parameter ones -- 82 -> 152 us at 4096 rows)
+    static const int64_t kSmallBytes = std::getenv("STN_SMALL_BYTES") ? std::atoll(std::getenv("STN_SMALL_BYTES")) : 64 * 1024;
+    static const int64_t kSmallRows = std::getenv("STN_SMALL_ROWS") ? std::atoll(std::getenv("STN_SMALL_ROWS")) : 2048;
     if (layout == STN_LAYOUT_AOS && n <= kSmallRows && n * P * (int64_t)sizeof(double) <= kSmallBytes) {
         if (!ctx->small_in) STN_CUDA(cudaHostAlloc((void**)&ctx->small_in, kSmallBytes, cudaHostAllocMapped));
         if (!ctx->small_out) STN_CUDA(cudaHostAlloc((void**)&ctx->small_out, kSmallRows * sizeof(double), cudaHostAllocMapped));
