@@ -89,7 +89,8 @@ def run(refepoch, initsfile, pmparin, parfile, *args, shares=None, pmparin_preli
     with open(samplefile, 'w') as f:
         f.write(' '.join(keys + ['log_likelihood', 'log_prior']) + '\n')
         np.savetxt(f, np.column_stack([chain, lnprob - lnprior, lnprior]), fmt='%.17g')
-    med, chi_sq, rchsq, estimates = summary.make_a_summary_of_bayesian_inference(samplefile, like)
+    med, chi_sq, rchsq, estimates = summary.make_a_summary_of_bayesian_inference(
+        samplefile, like, samples=sampler.chain.reshape(-1, prior.ndim), names=keys)        # summarised on the device
     result = dict(keys=keys, samplefile=samplefile, estimates=estimates, medians=med, chi_sq=chi_sq, rchsq=rchsq,
                   acceptance_fraction=sampler.acceptance_fraction, n_samples=len(chain))
     like.close()

@@ -84,20 +84,70 @@ def read_posterior_samples(samplefile):
     return names, data
 
 
+def _is_cuda_tensor(x):
+    return type(x).__module__.startswith('torch') and getattr(x, 'is_cuda', False)
+
+
+class _DeviceStats(object):
+    """Order statistics and correlations of an (n, P) CUDA chain computed on the device: one sort of all
+    columns, the same index arithmetic as the host functions above, only the few numbers needed come back.
+    Large ensembles produce millions of samples; the reference sorts every column (and, for om_asc, 360
+    re-ordered copies of it) in numpy (others.py:308-374)."""
+
+    def __init__(self, samples):
+        import torch
+        self.torch = torch
+        self.x = samples.to(torch.float64)
+        self.sorted = torch.sort(self.x, dim=0).values
+        self.n = int(self.x.shape[0])
+        self.corr = torch.corrcoef(self.x.T).cpu().numpy() if self.x.shape[1] > 1 else np.ones((1, 1))
+
+    def median(self, i):
+        a, n = self.sorted[:, i], self.n
+        return float(0.5 * (a[n // 2 - 1] + a[n // 2])) if n % 2 == 0 else float(a[(n - 1) // 2])
+
+    def median_range(self, i, confidencelevel):
+        a = self.sorted[:, i]
+        SV = _significant_volume(self.n, confidencelevel)
+        start = int((self.n - SV) / 2 - 1)
+        return float(a[start]), float(a[start + SV])
+
+    def periodic(self, i, period=360, confidencelevel=1):
+        torch = self.torch
+        a = self.sorted[:, i] % period
+        SV = _significant_volume(self.n, confidencelevel)
+        m = self.n - SV - 1
+        best = (None, float('inf'), None)
+        for threshold in np.arange(0, period, period / 360.):
+            k = int(torch.argmin(torch.abs(a - threshold)))
+            r = torch.sort(torch.cat((a[k:] - period, a[:k]))).values
+            widths = r[SV:SV + m] - r[:m]
+            j = int(torch.argmin(widths))                         # first minimum, as numpy's argmin
+            lo, hi = float(r[j]), float(r[j + SV])
+            value, error, median = 0.5 * (lo + hi), 0.5 * (hi - lo), float(r[int(j + SV / 2.)])
+            if error < best[1]:
+                best = (value, error, median)
+        value, error, median = best
+        return median % period, value + error - median, median - (value - error)
+
+
 def brief_summary(names, samples):
-    """(dict_median, text) for parameter columns `names` of the (n, len(names)) sample array."""
+    """(dict_median, text) for parameter columns `names` of the (n, len(names)) sample array -- a numpy array,
+    or a CUDA tensor (the chain of sampler.FusedEnsembleSampler), in which case sorting, order statistics
+    and correlations run on the device."""
     dict_median = {}
     out = ['#Medians of the simulated samples:\n',
            '#(Units: px in mas; mu_a and mu_d in mas/yr; incl in rad.)\n']
+    dev = _DeviceStats(samples) if _is_cuda_tensor(samples) else None
     for i, p in enumerate(names):
-        col = samples[:, i]
+        col = None if dev is not None else samples[:, i]
         if 'om_asc' in p:
-            med, up, low = periodic_sample2estimate(col)
+            med, up, low = dev.periodic(i) if dev is not None else periodic_sample2estimate(col)
             dict_median[p] = med
             out.append('%s = %f + %f - %f (deg)\n' % (p, med, up, low))
             continue
-        med = sample2median(col)
-        lo, hi = sample2median_range(col, 1)
+        med = dev.median(i) if dev is not None else sample2median(col)
+        lo, hi = dev.median_range(i, 1) if dev is not None else sample2median_range(col, 1)
         dict_median[p] = med
         if 'ra' in p:
             k = 180 / np.pi / 15
@@ -112,17 +162,22 @@ def brief_summary(names, samples):
     out.append('\n#Correlation coefficients:\n')
     for i in range(1, len(names)):
         for j in range(i):
-            r = np.corrcoef(samples[:, j], samples[:, i])[0, 1]
+            r = dev.corr[j, i] if dev is not None else np.corrcoef(samples[:, j], samples[:, i])[0, 1]
             out.append('r__%s__%s = %f\n' % (names[j], names[i], r))
     return dict_median, ''.join(out)
 
 
-def make_a_summary_of_bayesian_inference(samplefile, likelihood, outputfile=None):
+def make_a_summary_of_bayesian_inference(samplefile, likelihood, outputfile=None, samples=None, names=None):
     """Writes bayesian_estimates.dat next to `samplefile` (simulate.py:244-250): the brief
     summary plus chi-square / reduced chi-square at the medians (device kernel) and the
-    reference epoch.  Returns (dict_median, chi_sq, reduced chi_sq, path)."""
-    names, data = read_posterior_samples(samplefile)
-    names, data = names[:-2], data[:, :-2]
+    reference epoch.  `samples` / `names`: the chain itself (numpy or CUDA tensor, parameter columns only)
+    when it is still at hand -- a CUDA chain is summarised on the device; otherwise the file is read.
+    Returns (dict_median, chi_sq, reduced chi_sq, path)."""
+    if samples is None:
+        names, data = read_posterior_samples(samplefile)
+        names, data = names[:-2], data[:, :-2]
+    else:
+        data = samples
     dict_median, text = brief_summary(names, data)
     chi_sq, rchsq = likelihood.calculate_reduced_chi_square(dict_median)
     text += '\nchi-square = %f\nreduced chi-square = %f\n' % (chi_sq, rchsq)

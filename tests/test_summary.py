@@ -49,3 +49,24 @@ def test_full_summary_file_matches_reference(post, tmp_path):
     med, chi, rchi, out = summary.make_a_summary_of_bayesian_inference(str(p), like)
     assert open(out).read() == post['bayesian_estimates']
     like.close()
+
+
+@pytest.mark.gpu
+def test_device_summary_equals_host_summary():
+    """brief_summary on a CUDA chain (device sort / order statistics / correlations / periodic estimate)
+    writes the same text as the host path -- on the reference's recorded posterior and on a large chain."""
+    import torch
+    from sterne_b200 import summary
+    names = ['dec_0', 'incl_0', 'mu_a_0', 'mu_d_0', 'om_asc_0', 'px_0', 'ra_0']
+    rng = np.random.default_rng(7)
+    for n in (1501, 200000):
+        cols = [0.37 + 4e-10 * rng.standard_normal(n), 1.2 + 0.15 * rng.standard_normal(n),
+                -3.2 + 0.05 * rng.standard_normal(n), 7.9 + 0.06 * rng.standard_normal(n),
+                (350.0 + 25.0 * rng.standard_normal(n)) % 360.0, 1.25 + 0.04 * rng.standard_normal(n),
+                5.1 + 3e-10 * rng.standard_normal(n)]
+        cols[3] = cols[3] + 0.5 * (cols[2] + 3.2)
+        host = np.stack(cols, axis=1)
+        med_h, text_h = summary.brief_summary(names, host)
+        med_d, text_d = summary.brief_summary(names, torch.from_numpy(host).cuda())
+        assert text_d == text_h, n
+        assert med_d == med_h
