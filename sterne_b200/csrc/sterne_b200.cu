@@ -91,6 +91,9 @@
 #endif
 // EFAC: exponent budget (bits) the running product of variances may drift between two
 // renormalisations; the double range is +-1022 and T stays within 2^-100 .. 2^20 of Q.
+#ifndef STN_SAMPLER_SOURCE_LANES
+#define STN_SAMPLER_SOURCE_LANES 1     /* fused sampler: spread the sources of a joint fit over lanes of a warp */
+#endif
 #ifndef STN_SAMPLER_CLUSTER
 #define STN_SAMPLER_CLUSTER 1          /* fused sampler: one thread-block cluster + hardware barrier when <= 16 CTAs */
 #endif

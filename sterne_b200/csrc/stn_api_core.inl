@@ -136,6 +136,11 @@ int stn_create(const StnProblem* pb, int device, StnCtx** out_ctx) {
     int rc;
     if ((rc = upload(ctx, src.data(), src.size(), &P.src))) return bail(rc);
     if ((rc = upload(ctx, chunks.data(), chunks.size(), &P.chunks))) return bail(rc);
+    {
+        std::vector<int> first(pb->n_sources + 1, (int)chunks.size());
+        for (int c = (int)chunks.size() - 1; c >= 0; --c) first[chunks[c].source] = c;
+        if ((rc = upload(ctx, first.data(), first.size(), &P.first_chunk))) return bail(rc);
+    }
     if ((rc = upload(ctx, pb->a1dot_source, (size_t)pb->n_a1dot, &P.a1_src))) return bail(rc);
     if ((rc = upload(ctx, pb->a1dot_mu, (size_t)pb->n_a1dot, &P.a1_mu))) return bail(rc);
     if ((rc = upload(ctx, pb->a1dot_sigma, (size_t)pb->n_a1dot, &P.a1_sigma))) return bail(rc);

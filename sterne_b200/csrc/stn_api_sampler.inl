@@ -56,12 +56,13 @@ int stn_ensemble_run(StnCtx* ctx, double* x_dev, double* lp_dev, int64_t n_walke
         return fail(STN_ERR_INVALID, "the persistent sampler kernel needs mode fast, plan 0 or lanes=1|splits=1, P <= %d",
                     STN_SAMPLER_MAX_P);
     bool fuse = engine == 1 || (engine == 0 && can_fuse && evals <= 512);
-    int grid = 0;
+    int grid = 0, lanes = 1;
     size_t smem = 0;
     if (fuse) {
         // shared-memory image of the problem (sampler_stage_problem's layout)
         const ProbDev& pp = ctx->prior_prob;
-        smem = sampler_align(sizeof(SrcDev) * pp.n_sources) + sampler_align(sizeof(ChunkDev) * pp.n_chunks);
+        smem = sampler_align(sizeof(SrcDev) * pp.n_sources) + sampler_align(sizeof(ChunkDev) * pp.n_chunks) +
+               sampler_align(sizeof(int) * (pp.n_sources + 1));
         for (int e : ctx->n_epochs) smem += sampler_align(sizeof(double) * STN_FAST_ROW * (size_t)e);
         smem += 3 * sampler_align(8 * (size_t)pp.n_a1dot) + 3 * sampler_align(8 * (size_t)pp.n_sini) +
                 3 * sampler_align(8 * (size_t)pp.n_prior) + 3 * sampler_align(8 * (size_t)pp.n_sinlim);
@@ -74,7 +75,13 @@ int stn_ensemble_run(StnCtx* ctx, double* x_dev, double* lp_dev, int64_t n_walke
         int per_sm = 0;
         STN_CUDA(cudaFuncSetAttribute(stn_ensemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         STN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stn_ensemble_kernel, kSamplerThreads, smem));
-        const int64_t want = (H + kSamplerThreads - 1) / kSamplerThreads;
+        // lanes per walker: the sources of a joint fit are spread over up to 8 lanes of a warp
+        lanes = 1;
+        if (STN_SAMPLER_SOURCE_LANES && ctx->prob.n_sources > 1) {
+            while (lanes < 8 && lanes < ctx->prob.n_sources) lanes *= 2;
+            if ((ctx->prob.n_sources + lanes - 1) / lanes > kSamplerMaxSourcesPerLane) lanes = 1;
+        }
+        const int64_t want = (H * lanes + kSamplerThreads - 1) / kSamplerThreads;
         const int64_t cap = (int64_t)per_sm * ctx->sm_count;
         if (cap < 1) {
             if (engine == 1) return fail(STN_ERR_CUDA, "the persistent sampler kernel does not fit on this device");
@@ -107,7 +114,7 @@ int stn_ensemble_run(StnCtx* ctx, double* x_dev, double* lp_dev, int64_t n_walke
                 cfg.attrs = at;
                 cfg.numAttrs = 1;
                 const cudaError_t e = cudaLaunchKernelEx(&cfg, stn_ensemble_kernel, prob, x_dev, lp_dev, n_walkers, ld, a, seed,
-                                                         step0, n_steps, thin, chain_dev, lnprob_dev, nacc, 1);
+                                                         step0, n_steps, thin, chain_dev, lnprob_dev, nacc, 1, lanes);
                 if (e == cudaSuccess) {
                     ctx->launches++;
                     return STN_OK;
@@ -117,7 +124,7 @@ int stn_ensemble_run(StnCtx* ctx, double* x_dev, double* lp_dev, int64_t n_walke
         }
         int cluster_mode = 0;
         void* args[] = {&prob, &x_dev, &lp_dev, &n_walkers, &ld, &a, &seed, &step0, &n_steps, &thin, &chain_dev,
-                        &lnprob_dev, &nacc, &cluster_mode};
+                        &lnprob_dev, &nacc, &cluster_mode, &lanes};
         STN_CUDA(cudaLaunchCooperativeKernel((const void*)stn_ensemble_kernel, dim3((unsigned)grid), dim3(kSamplerThreads), args, smem, st));
         ctx->launches++;
         return STN_OK;

@@ -54,6 +54,7 @@ struct ProbDev {
     const double* sinlim_hi;
     const SrcDev* src;
     const ChunkDev* chunks;
+    const int* first_chunk;           // [n_sources + 1]: chunks of source s are first_chunk[s] .. first_chunk[s + 1] - 1
     const int* a1_src;
     const double* a1_mu;
     const double* a1_sigma;
@@ -445,7 +446,9 @@ struct SrcState {
     int nvar;     // EFAC: epochs this lane has folded into Q since src_begin
 };
 
-template <int R, bool COH>
+// WARP: all 32 lanes are here together working on the SAME source (K1, the one-lane-per-walker sampler), so the
+// renormalisation cadence can be made warp-uniform; false when lanes of a warp work on different sources
+template <int R, bool COH, bool WARP = true>
 __device__ __forceinline__ void src_begin(const ProbDev& P, const SrcDev& S, const double* __restrict__ theta,
                                           const int64_t (&nidx)[R], int64_t ld, int layout, SrcState<R>& st) {
     const bool ef = S.efac_on != 0;
@@ -462,7 +465,7 @@ __device__ __forceinline__ void src_begin(const ProbDev& P, const SrcDev& S, con
     }
     // the cadence only has to be uniform over the warp (the epoch loops stay converged); it
     // never changes a bit of the result
-    st.mask = ef ? __reduce_min_sync(0xffffffffu, m) : m;
+    st.mask = (ef && WARP) ? __reduce_min_sync(0xffffffffu, m) : m;
     st.nvar = 0;
 }
 
@@ -478,10 +481,11 @@ __device__ __forceinline__ void src_chunk(const SrcDev& S, const double* __restr
     if (ef) st.nvar += sub < n_epochs ? (n_epochs - sub + L - 1) / L : 0;
 }
 
-// log_p += -0.5*sum((res/errs)^2); log_p += -sum(log(errs))  (simulate.py:370-371)
+// The two terms one source adds to log L:  -0.5*sum((res/errs)^2)  and  -sum(log(errs))  (simulate.py:370-371);
+// in chi-square mode the first is the chi-square itself and the second zero.
 template <int R, int L>
-__device__ __forceinline__ void src_fold(const ProbDev& P, const SrcDev& S, bool source_ends, SrcState<R>& st,
-                                         double (&logl)[R]) {
+__device__ __forceinline__ void src_fold_terms(const ProbDev& P, const SrcDev& S, bool source_ends, SrcState<R>& st,
+                                               double (&term_chi)[R], double (&term_logdet)[R]) {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         double chi, logdet;
@@ -497,12 +501,20 @@ __device__ __forceinline__ void src_fold(const ProbDev& P, const SrcDev& S, bool
             // host constant, counted once: by the split that holds the source's last chunk
             logdet = source_ends ? S.neg_sum_log_err : 0.0;
         }
-        if (P.out_chisq) {
-            logl[r] += chi;
-        } else {
-            logl[r] += -0.5 * chi;
-            logl[r] += logdet;
-        }
+        term_chi[r] = P.out_chisq ? chi : -0.5 * chi;
+        term_logdet[r] = P.out_chisq ? 0.0 : logdet;
+    }
+}
+
+template <int R, int L>
+__device__ __forceinline__ void src_fold(const ProbDev& P, const SrcDev& S, bool source_ends, SrcState<R>& st,
+                                         double (&logl)[R]) {
+    double a[R], b[R];
+    src_fold_terms<R, L>(P, S, source_ends, st, a, b);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        logl[r] += a[r];
+        if (!P.out_chisq) logl[r] += b[r];
     }
 }
 

@@ -190,6 +190,56 @@ __device__ double logpost_one(const ProbDev& P, const double* theta_row, int64_t
     return v;
 }
 
+// The same log-posterior with the SOURCES of one walker spread over LS lanes of a warp (lane `sub` of the group
+// takes sources sub, sub + LS, ...): the per-source prologue, epoch loop and fold are independent, so a joint fit
+// of S sources takes about the time of its longest source instead of the sum.  Every lane returns the full
+// value: the two terms of each source are fetched from their owner with shuffles and added in source order,
+// exactly as the one-lane form (and K1) adds them -- same bits.
+constexpr int kSamplerMaxSourcesPerLane = 8;
+
+template <bool COH>
+__device__ double logpost_lanes(const ProbDev& P, const double* theta_row, int64_t ld, int sub, int LS) {
+    double ta[kSamplerMaxSourcesPerLane], tb[kSamplerMaxSourcesPerLane];
+#pragma unroll
+    for (int j = 0; j < kSamplerMaxSourcesPerLane; ++j) ta[j] = tb[j] = 0.0;
+    const int64_t nidx[1] = {0};
+    SrcState<1> st;
+    st.mask = kChunk - 1;
+    st.nvar = 0;
+    // lane `sub` walks ITS j-th source while the other lanes of the group walk theirs: the same code at the same
+    // time on different sources (a loop over the common chunk list would serialise the lanes instead)
+    for (int j = 0; j * LS < P.n_sources; ++j) {
+        const int s = j * LS + sub;
+        if (s >= P.n_sources) continue;
+        const SrcDev& S = P.src[s];
+        src_begin<1, COH, false>(P, S, theta_row, nidx, ld, STN_LAYOUT_AOS, st);
+        for (int c = P.first_chunk[s]; c < P.first_chunk[s + 1]; ++c) {
+            const ChunkDev ck = P.chunks[c];
+            src_chunk<1, 1>(S, ck.rows, ck.n_epochs, 0, st);
+        }
+        double a[1], b[1];
+        src_fold_terms<1, 1>(P, S, true, st, a, b);
+        ta[j] = a[0];
+        tb[j] = b[0];
+    }
+    __syncwarp();
+    const int base = (threadIdx.x & 31) & ~(LS - 1);
+    double v = 0.0;
+    for (int j = 0; j * LS < P.n_sources; ++j)
+        for (int o = 0; o < LS && j * LS + o < P.n_sources; ++o) {
+            const double va = __shfl_sync(0xffffffffu, ta[j], base + o);
+            const double vb = __shfl_sync(0xffffffffu, tb[j], base + o);
+            v += va;
+            v += vb;
+        }
+    if (P.n_a1dot > 0 || P.n_sini > 0) v += constraint_terms<COH>(P, theta_row, 0, ld, STN_LAYOUT_AOS);
+    if (P.n_prior > 0) {
+        const double lp = prior_terms<COH>(P, theta_row, 0, ld, STN_LAYOUT_AOS);
+        v = (lp == -CUDART_INF) ? lp : v + lp;
+    }
+    return v;
+}
+
 // Bytes of shared memory sampler_stage_problem needs (host and device agree through this one function).
 __host__ __device__ inline size_t sampler_align(size_t v) { return (v + 15) & ~(size_t)15; }
 
@@ -240,6 +290,7 @@ __device__ ProbDev sampler_stage_problem(const ProbDev& P, unsigned char* smem) 
     };
     Q.src = src;
     Q.chunks = chunks;
+    Q.first_chunk = reinterpret_cast<const int*>(take(P.first_chunk, sizeof(int) * (P.n_sources + 1)));
     Q.a1_src = reinterpret_cast<const int*>(take(P.a1_src, sizeof(int) * P.n_a1dot));
     Q.a1_mu = reinterpret_cast<const double*>(take(P.a1_mu, sizeof(double) * P.n_a1dot));
     Q.a1_sigma = reinterpret_cast<const double*>(take(P.a1_sigma, sizeof(double) * P.n_a1dot));
@@ -274,7 +325,8 @@ __device__ __forceinline__ void sampler_barrier(bool cluster_mode) {
 __global__ void __launch_bounds__(kSamplerThreads)
 stn_ensemble_kernel(const ProbDev P0, double* x, double* lp, const int64_t W, const int64_t ld, const double a,
                     const uint64_t seed, const uint64_t step0, const int64_t n_steps, const int64_t thin,
-                    double* chain, double* lnprob, unsigned long long* n_accept, const int cluster_mode) {
+                    double* chain, double* lnprob, unsigned long long* n_accept, const int cluster_mode,
+                    const int LS) {
     // The whole problem description -- sources, chunk list, epoch tables, constraints, prior -- is copied
     // to shared memory once: the barrier between half-steps invalidates L1 (acquire), so anything left in
     // global memory would be re-fetched from L2 (~700 cycles per dependent load) in every half-step.
@@ -316,15 +368,15 @@ stn_ensemble_kernel(const ProbDev P0, double* x, double* lp, const int64_t W, co
         d.lnu = log(u01(r[0], r[1]));
     };
     // The part that needs the partner's CURRENT position: proposal, log-posterior, accept / reject.
-    auto finish = [&](const Draw& d) {
+    auto finish = [&](const Draw& d, int sub) {
         const double* xj = x + d.jrow * ld;
         for (int p = 0; p < np; ++p) {
             const double vj = __ldcg(xj + p);
             y[p] = fma(d.z, y[p] - vj, vj);
         }
-        const double lpy = logpost_one<true>(P, y, np);
+        const double lpy = LS > 1 ? logpost_lanes<true>(P, y, np, sub, LS) : logpost_one<true>(P, y, np);
         const double lnq = (double)(np - 1) * d.logz + lpy - d.lp_i;
-        if (d.valid && (lpy > -CUDART_INF) && (lpy == lpy) && (d.lnu < lnq)) {
+        if (d.valid && sub == 0 && (lpy > -CUDART_INF) && (lpy == lpy) && (d.lnu < lnq)) {
             for (int p = 0; p < np; ++p) x[d.i * ld + p] = y[p];
             lp[d.i] = lpy;
             ++accepted;
@@ -340,7 +392,7 @@ stn_ensemble_kernel(const ProbDev P0, double* x, double* lp, const int64_t W, co
             for (int64_t w = gtid; w < W; w += nthreads) lnprob[slot * W + w] = __ldcg(lp + w);
     };
 
-    if (cluster_mode != 0 && Hpad <= nthreads) {
+    if (cluster_mode != 0 && LS == 1 && Hpad <= nthreads) {
         // One proposal per thread and a hardware cluster barrier: the barrier is SPLIT.  After a thread has
         // stored its accepted walker it arrives, prepares its next proposal (two Philox draws, its own row from
         // L2, two logarithms) while the other CTAs finish, and only then waits -- the barrier's latency and the
@@ -350,7 +402,7 @@ stn_ensemble_kernel(const ProbDev P0, double* x, double* lp, const int64_t W, co
         if (active) prepare(gtid, step0, 0, d);
         for (int64_t t = 0; t < n_steps; ++t) {
             for (int half = 0; half < 2; ++half) {
-                if (active) finish(d);
+                if (active) finish(d, 0);
                 asm volatile("barrier.cluster.arrive.release;" ::: "memory");
                 const bool more = !(t == n_steps - 1 && half == 1);
                 if (active && more) prepare(gtid, step0 + (uint64_t)(half ? t + 1 : t), half ^ 1, d);
@@ -362,13 +414,19 @@ stn_ensemble_kernel(const ProbDev P0, double* x, double* lp, const int64_t W, co
             }
         }
     } else {
+        // general form: a thread may walk several proposals; with LS > 1 a group of LS lanes shares one proposal
+        // (every lane draws the same numbers and builds the same proposal, the sources are split, lane 0 stores)
+        const int64_t slot = gtid / LS, n_slots = nthreads / LS;
+        const int sub = (int)(gtid % LS);
+        const int per_warp = 32 / LS;
+        const int64_t Hgrp = (H + per_warp - 1) / per_warp * per_warp;      // whole warps walk the loop together
         for (int64_t t = 0; t < n_steps; ++t) {
             const uint64_t step = step0 + (uint64_t)t;
             for (int half = 0; half < 2; ++half) {
-                for (int64_t kk = gtid; kk < Hpad; kk += nthreads) {
+                for (int64_t kk = slot; kk < Hgrp; kk += n_slots) {
                     Draw d;
                     prepare(kk, step, half, d);
-                    finish(d);
+                    finish(d, sub);
                 }
                 sampler_barrier(cluster_mode != 0);        // the other half reads these walkers next
             }

@@ -222,6 +222,21 @@ def test_fused_sampler_matches_torch_sampler_statistically():
     assert torch.equal(a3.chain, b3.chain) and torch.equal(a3.lnprob, b3.lnprob)
     assert 0.02 < a3.acceptance_fraction < 0.98
     like3.close()
+    # joint fits: the persistent kernel spreads the SOURCES of a walker over lanes of a warp (5 sources -> 8 lanes,
+    # 3 -> 4, 2 -> 2) and still sums them in source order: same chain as the launch engine
+    for case4, nw4 in ((synthetic.config4(), 250), (synthetic.config5('C', n_sources=3, n_epochs=40), 130),
+                       (synthetic.config5('B', n_sources=2, n_epochs=30), 64)):
+        like4 = case4.likelihood()
+        prior4 = BoxPrior({kname: [case4.box[kname][0], case4.box[kname][1], 'Uniform'] for kname in case4.names})
+        half4 = np.array([0.5 * (case4.box[kname][1] - case4.box[kname][0]) for kname in case4.names])
+        p4 = case4.truth_vector() + 0.02 * half4 * np.random.default_rng(6).standard_normal((nw4, case4.n_params))
+        a4 = FusedEnsembleSampler(like4, prior4, nw4, seed=8, engine='persistent')
+        a4.run(p4, 30, thin=3)
+        b4 = FusedEnsembleSampler(like4, prior4, nw4, seed=8, engine='launches', plan=make_plan(1, 1))
+        b4.run(p4, 30, thin=3)
+        assert torch.equal(a4.chain, b4.chain) and torch.equal(a4.lnprob, b4.lnprob), case4.name
+        assert a4.acceptance_fraction == b4.acceptance_fraction
+        like4.close()
     like.close()
 
 
