@@ -69,6 +69,37 @@ class BoxPrior(object):
                 out[:, j] = np.arccos(np.cos(self.a[j]) - u * (np.cos(self.a[j]) - np.cos(self.b[j])))
         return out
 
+    def prior_transform(self, u):
+        """Unit hypercube -> parameter space, (ndim,) or (N, ndim), numpy or torch: what nested samplers
+        (dynesty, bilby's dynesty wrapper) ask a prior for.  Uniform: a + (b - a) u; Gaussian: inverse normal
+        CDF; Sine: arccos(cos a - u (cos a - cos b)).  The sin(incl) limits are a constraint, not a
+        transform: points outside them get log-likelihood -inf from `log_prob_fn` / `stn_logpost`."""
+        if _is_torch(u):
+            import torch
+            x = u.clone().to(torch.float64)
+            cols = x if x.dim() == 2 else x[None, :]
+            for j, kind in enumerate(self.kinds):
+                a, b = float(self.a[j]), float(self.b[j])
+                if kind == 'Uniform':
+                    cols[:, j] = a + (b - a) * cols[:, j]
+                elif kind == 'Gaussian':
+                    cols[:, j] = a + b * math.sqrt(2.0) * torch.erfinv(2.0 * cols[:, j] - 1.0)
+                else:
+                    cols[:, j] = torch.arccos(math.cos(a) - cols[:, j] * (math.cos(a) - math.cos(b)))
+            return x
+        from scipy.special import erfinv
+        x = np.array(u, dtype=np.float64, copy=True)
+        cols = x if x.ndim == 2 else x[None, :]
+        for j, kind in enumerate(self.kinds):
+            a, b = self.a[j], self.b[j]
+            if kind == 'Uniform':
+                cols[:, j] = a + (b - a) * cols[:, j]
+            elif kind == 'Gaussian':
+                cols[:, j] = a + b * math.sqrt(2.0) * erfinv(2.0 * cols[:, j] - 1.0)
+            else:
+                cols[:, j] = np.arccos(np.cos(a) - cols[:, j] * (np.cos(a) - np.cos(b)))
+        return x
+
     def log_prob(self, theta):
         """(N, ndim) -> (N,) log prior density (−inf outside the support)."""
         if _is_torch(theta):

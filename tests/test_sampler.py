@@ -32,6 +32,29 @@ def test_box_prior_numpy_torch_and_normalisation():
     assert np.isfinite(pc.log_prob(pts)[0]) and np.isinf(pc.log_prob(pts)[1])
 
 
+def test_prior_transform_maps_the_unit_cube_onto_the_prior():
+    """prior_transform (what dynesty asks for): uniform numbers in -> samples of the prior out, numpy == torch,
+    1-D points and batches; checked through each marginal's CDF."""
+    pr = BoxPrior(LIMITS, {'sin_incl_limits_constraints': {}})
+    rng = np.random.default_rng(3)
+    u = rng.random((20000, 3))
+    x = pr.prior_transform(u)
+    xt = pr.prior_transform(torch.from_numpy(u)).numpy()
+    assert np.allclose(x, xt, rtol=1e-12, atol=1e-12)
+    assert np.array_equal(pr.prior_transform(u[7]), x[7]) and u[7, 0] != x[7, 0]           # input left untouched
+    assert np.isfinite(pr.log_prob(x)).all()                                                # inside the support
+    # Uniform(0.5, 2.5), Gaussian(-3, 0.7), Sine(0.2, 2.9): empirical CDFs at a few points
+    assert abs((x[:, 0] < 1.0).mean() - 0.25) < 0.01
+    assert abs((x[:, 1] < -3.0).mean() - 0.5) < 0.01 and abs(x[:, 1].std() - 0.7) < 0.02
+    cdf_sine = lambda t: (np.cos(0.2) - np.cos(t)) / (np.cos(0.2) - np.cos(2.9))
+    for t in (0.8, 1.5, 2.2):
+        assert abs((x[:, 2] < t).mean() - cdf_sine(t)) < 0.01
+    # monotone in every coordinate (a valid inverse CDF)
+    g = np.linspace(0.001, 0.999, 50)
+    grid = pr.prior_transform(np.stack([g, g, g], axis=1))
+    assert (np.diff(grid, axis=0) > 0).all()
+
+
 def test_batch_pool_is_one_batched_call():
     calls = []
 
